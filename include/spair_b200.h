@@ -1,0 +1,242 @@
+/*
+ * spair_b200.h — C-ABI of libspair_b200.so: the sm_100a kernels behind SPAIR's per-cell
+ * object pipeline (sample -> glimpse -> render, forward and backward).
+ *
+ * The reference (yonkshi/SPAIR_pytorch) has no FFI of its own: the path sits behind the
+ * Python API of spair/models.py and spair/modules.py.  Each entry point below replaces a
+ * block of that Python, cited as file:line, and is what a binding for this path would
+ * call (see INTEGRATION.md for the ctypes stubs).  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to fp32 unless its
+ *     comment says "host"; the library never allocates, never synchronises, keeps no
+ *     global state and is re-entrant; `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, a positive cudaError_t from the launch, or
+ *     SPAIR_ERR_INVALID (-1) for a rejected argument (nothing is launched then);
+ *   - "image-major" buffers are indexed [b][cell][...] with cell = h*Wc + w (the layout
+ *     `to_H_W_C(z).view(-1, k)` produces at models.py:468,474);
+ *   - "rows" of a wavefront are indexed r = k*B + b for the k-th cell in `cells`
+ *     (cells with equal w + (L+1)*h are mutually independent).
+ */
+#ifndef SPAIR_B200_H
+#define SPAIR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPAIR_ERR_INVALID (-1)
+#define SPAIR_MAX_NEIGHBOURS 12
+#define SPAIR_ABI_VERSION 1
+
+int spair_abi_version(void);
+
+/* Box decode constants (host struct).  models.py:339-374, config.py:34,38-41. */
+typedef struct spair_box_geom {
+    float yx_scale;     /* MAX_YX - MIN_YX */
+    float yx_min;       /* MIN_YX */
+    float hw_scale;     /* MAX_HW - MIN_HW */
+    float hw_min;       /* MIN_HW */
+    float anchor;       /* ANCHORBOX_SHAPE[0] (the reference uses [0] for both axes, models.py:366) */
+    float img_h, img_w; /* INPUT_IMAGE_SHAPE[1], [2] */
+    float cell_ratio_y; /* (float)(pixels_per_cell[0] / image_height), models.py:373 */
+    float cell_ratio_x; /* (float)(pixels_per_cell[1] / image_width),  models.py:374 */
+} spair_box_geom;
+
+/* ------------------------------------------------------------------------------------
+ * L0  lateral context.  Replaces SPAIR._get_sequential_context (models.py:292-320) plus the
+ * torch.cat((cell_feat, context)) at models.py:76 for all cells of one wavefront.
+ * Writes [feat(F) | ctx(n_nb*(A+6))] for every row into up to three destinations (the input
+ * buffers of box_network, z_network and obj_network; models.py:76,88,100).  A neighbour
+ * outside the grid contributes `edge` (virtual_edge_element, models.py:273-290,316).
+ * ---------------------------------------------------------------------------------- */
+int spair_context_gather_fwd(const float* feat,            /* [B,F,Hc,Wc] backbone output */
+                             const float* box,             /* [B,HW,4] image-major */
+                             const float* attr,            /* [B,HW,A] */
+                             const float* depth,           /* [B,HW]   */
+                             const float* pres,            /* [B,HW]   */
+                             const float* edge,            /* [A+6]    */
+                             const int* cells, int n_cells,
+                             const int* nb_offsets, int n_nb, /* host: n_nb pairs (dh,dw) */
+                             int B, int F, int Hc, int Wc, int A,
+                             float* dst0, int ld0, float* dst1, int ld1, float* dst2, int ld2,
+                             void* stream);
+
+/* Backward of the context concat, as a gather at the PRODUCER cell (deterministic, no
+ * atomics): for every row of this wavefront sums, over the later cells that consumed it,
+ * the context slices of up to three MLP-input gradient buffers.
+ *   out[r, 0:A+6] = sum_{nb} sum_{s<3} dX_s[row(consumer), col0 + nb*(A+6) + j]           */
+int spair_context_grad_gather(const float* dx0, int ld0, const float* dx1, int ld1,
+                              const float* dx2, int ld2, /* [HW*B, ld] wavefront-major, any may be NULL */
+                              int col0,                  /* column where the context block starts (= F) */
+                              const int* cells, int n_cells,
+                              const int* wf_pos,         /* [HW] position of each cell in wavefront-major order */
+                              const int* nb_offsets, int n_nb, /* host */
+                              int B, int Hc, int Wc, int A,
+                              float* out, int ld_out,    /* [n_cells*B, >=A+6] */
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * L1+L2  box head.  Replaces latent_to_mean_std (modules.py:167-176), _freeze_learning
+ * (models.py:413-429), the four _sample_z calls and SPAIR._build_box (models.py:322-381).
+ * y[:,0:4] = means (cy,cx,h,w), y[:,4:8] = log-stds; y[:,8:8+n_pt] = passthrough features,
+ * copied to pt_dst (torch.cat at models.py:88).
+ * ---------------------------------------------------------------------------------- */
+int spair_box_head_fwd(const float* y, int ld_y,
+                       const float* eps,                  /* [B,HW,4] normal noise (cy,cx,h,w) */
+                       const int* cells, int n_cells, int B, int HW, int Wc,
+                       const spair_box_geom* geom,        /* host */
+                       float* box,                        /* [B,HW,4] (cell_x, cell_y, width, height) */
+                       float* z_where,                    /* [B,HW,4] (xt, yt, xs, ys) */
+                       float* dmean, float* dstd, int ld_dist, /* [B,HW,ld_dist]; cols 0..3 written */
+                       float* xdst0, int ldx0, float* xdst1, int ldx1, /* row-local copies of box (may be NULL) */
+                       int n_pt, float* pt_dst, int ld_pt,
+                       void* stream);
+
+/* d_y[:,0:8] = (1 - wheel) * chain rule; d_y[:,8:8+n_pt] = d_pt_src (passthrough grad). */
+int spair_box_head_bwd(const float* y, int ld_y, const float* eps,
+                       const int* cells, int n_cells, int B, int HW, int Wc,
+                       const spair_box_geom* geom, const float* wheel, /* device scalar: training wheel f */
+                       const float* d_box0, int ldb0, const float* d_box1, int ldb1,
+                       const float* d_box2, int ldb2,      /* row-local grads wrt box (may be NULL) */
+                       const float* d_zw_local, int ld_zwl, /* row-local grad wrt z_where (glimpse), may be NULL */
+                       const float* d_zw_img,              /* [B,HW,4] image-major grad wrt z_where (render), may be NULL */
+                       const float* d_dmean, const float* d_dstd, int ld_dist, /* image-major, may be NULL */
+                       int n_pt, const float* d_pt_src, int ld_pt,
+                       float* d_y,                        /* [rows, ld_y] */
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * L1/L3  Normal heads (z_what: width A, identity; z_depth: width 1, 4*sigmoid(clamp)).
+ * Replaces latent_to_mean_std + (_freeze_learning) + _sample_z (+ clamped_sigmoid) at
+ * models.py:83-85 and models.py:92-97.  y[:,0:W] means, y[:,W:2W] log-stds,
+ * y[:,2W:2W+n_pt] passthrough (z_network only).
+ * ---------------------------------------------------------------------------------- */
+int spair_normal_head_fwd(const float* y, int ld_y, int W,
+                          const float* eps,               /* [B,HW,W] */
+                          const int* cells, int n_cells, int B, int HW,
+                          int squash, float squash_scale,   /* squash: out = scale*sigmoid(clamp(z,-10,10)) */
+                          float* out,                     /* [B,HW,W] image-major */
+                          float* dmean, float* dstd, int ld_dist, /* pre-offset to this head's first column */
+                          float* xdst0, int ldx0, float* xdst1, int ldx1,
+                          int n_pt, float* pt_dst, int ld_pt,
+                          void* stream);
+
+int spair_normal_head_bwd(const float* y, int ld_y, int W, const float* eps,
+                          const int* cells, int n_cells, int B, int HW,
+                          int squash, float squash_scale,
+                          const float* wheel,             /* device scalar or NULL (= not frozen, attr) */
+                          const float* d_out0, int ldo0, const float* d_out1, int ldo1,
+                          const float* d_out2, int ldo2,  /* row-local grads wrt out */
+                          const float* d_out_img,         /* [B,HW,W] image-major, may be NULL */
+                          const float* d_dmean, const float* d_dstd, int ld_dist,
+                          int n_pt, const float* d_pt_src, int ld_pt,
+                          float* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * L4  presence head.  Replaces SPAIR._build_obj_pres (models.py:393-411).
+ * ---------------------------------------------------------------------------------- */
+int spair_pres_head_fwd(const float* y, int ld_y, const float* u /* [B,HW] uniform(0,1) */,
+                        const int* cells, int n_cells, int B, int HW,
+                        float* pres /* [B,HW] */, void* stream);
+
+int spair_pres_head_bwd(const float* y, int ld_y, const float* u,
+                        const int* cells, int n_cells, int B, int HW, const float* wheel,
+                        const float* d_pres_local, int ld_local, /* row-local (context), may be NULL */
+                        const float* d_pres_img,                 /* [B,HW] image-major, may be NULL */
+                        float* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * G  glimpse extractor = stn(image, z_where, [Gh,Gw], inverse=False) (modules.py:216-273)
+ * as called from SPAIR._encode_attr (models.py:383-391): fused affine_grid + bilinear
+ * grid_sample, border padding, align_corners=False.  cells == NULL: n_cells*B... is ignored
+ * and row r samples image r with z_where row r (the plain stn() call); otherwise row
+ * r = k*B + b samples image b with z_where[b, cells[k]].
+ * ---------------------------------------------------------------------------------- */
+int spair_glimpse_fwd(const float* image,                 /* [B,C,Ih,Iw] */
+                      const float* z_where,               /* [B,HW,4] image-major (or [B,4]) */
+                      const int* cells, int n_cells, int B, int HW,
+                      int C, int Ih, int Iw, int Gh, int Gw,
+                      float* out, int ld_out,             /* [rows, C*Gh*Gw] */
+                      void* stream);
+
+int spair_glimpse_bwd(const float* image, const float* z_where,
+                      const int* cells, int n_cells, int B, int HW,
+                      int C, int Ih, int Iw, int Gh, int Gw,
+                      const float* d_out, int ld_out,
+                      float* d_z_where_local,             /* [rows,4], overwritten */
+                      float* d_image,                     /* [B,C,Ih,Iw] accumulated with atomics, or NULL */
+                      void* stream);
+
+/* stn(image, z_where, [Oh,Ow], inverse=True) (modules.py:255-269): generic paste of n
+ * images [n,C,Gh,Gw] onto [n,C,Oh,Ow] canvases, zeros padding.  API-compat path; the model
+ * itself uses the fused renderer below. */
+int spair_paste_fwd(const float* image, const float* z_where, int n, int C, int Gh, int Gw,
+                    int Oh, int Ow, float* out, void* stream);
+int spair_paste_bwd(const float* image, const float* z_where, int n, int C, int Gh, int Gw,
+                    int Oh, int Ow, const float* d_out,
+                    float* d_image /* zero-filled by caller, accumulated */, float* d_z_where /* [n,4] overwritten */,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * R (+E)  fused renderer.  Replaces everything in SPAIR._render after the decoder MLP
+ * (models.py:481-540) including stn(..., inverse=True): logit scale/bias + analytical
+ * sigmoid, alpha *= z_pres, importance = max(alpha*z_depth, 0.01), inverse warp of
+ * colour / alpha / importance, importance-normalised alpha compositing over all HW objects
+ * and the final clamp — without materialising [N, C+2, Ih, Iw].  Optionally fuses the BCE of
+ * SPAIR._build_loss (models.py:547): per-tile partial sums of
+ * -(t*max(log p,-100) + (1-t)*max(log(1-p),-100)).
+ * ---------------------------------------------------------------------------------- */
+int spair_render_num_tiles(int B, int Ih, int Iw);  /* length of bce_partial */
+
+int spair_render_fwd(const float* logits,                 /* [B*HW, G, G, C+1] raw decoder output */
+                     const float* z_where,                /* [B*HW,4] */
+                     const float* z_depth, const float* z_pres, /* [B*HW] */
+                     int B, int HW, int C, int G, int Ih, int Iw,
+                     float obj_scale, float alpha_scale, float alpha_bias,
+                     float* recon,                        /* [B,C,Ih,Iw] */
+                     float* denom,                        /* [B,Ih,Iw]: sum_n(importance_n + 1e-9), negated where the clamp at 1 was active */
+                     const float* target, float* bce_partial, /* both NULL or both set */
+                     void* stream);
+
+/* Gradient wrt recon is d_recon (may be NULL) + bce_scale * dBCE/drecon(recon, target)
+ * (target may be NULL).  gs_ws is a [B,C+1,Ih,Iw] workspace. */
+int spair_render_bwd(const float* logits, const float* z_where, const float* z_depth,
+                     const float* z_pres, int B, int HW, int C, int G, int Ih, int Iw,
+                     float obj_scale, float alpha_scale, float alpha_bias,
+                     const float* recon, const float* denom,
+                     const float* d_recon, const float* target, const float* bce_scale /* device scalar or NULL (=1) */,
+                     float* gs_ws,
+                     float* d_logits, float* d_z_where, float* d_z_depth, float* d_z_pres,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K  KL terms.  Replaces SPAIR._compute_KL (models.py:169-262): z_pres-masked Normal KLs of
+ * the D = 4+A+1 latent columns against the priors of config.py:45-52, and the sequential
+ * count-prior scan for the presence KL.  count_dist0 is the normalised truncated geometric
+ * prior of models.py:184-193 ([HW+1], computed by the caller exactly as the reference does).
+ * kl_map[b,cell,0:D] Normal KLs, kl_map[b,cell,D] presence KL; kl_sums[b,0:7] per-name sums
+ * in the order cy, cx, height, width, attr, depth, pres (the `torch.sum(z_kl, dim=[1,2,3])`
+ * of models.py:553).
+ * ---------------------------------------------------------------------------------- */
+int spair_kl_fwd(const float* dmean, const float* dstd,   /* [B,HW,D] */
+                 const float* pres,                       /* [B,HW] (z_pres == z_pres_prob, models.py:409) */
+                 const float* prior_mean, const float* prior_std, /* [D] */
+                 const float* count_dist0,                /* [HW+1] */
+                 int B, int HW, int A,
+                 float* kl_map,                           /* [B,HW,D+1] */
+                 float* p_z,                              /* [B,HW] prior presence probability per cell */
+                 float* kl_sums,                          /* [B,7] */
+                 void* stream);
+
+int spair_kl_bwd(const float* dmean, const float* dstd, const float* pres,
+                 const float* prior_mean, const float* prior_std, const float* kl_map,
+                 const float* p_z, const float* d_sums /* [B,7] */, int B, int HW, int A,
+                 float* d_dmean, float* d_dstd, float* d_pres, void* stream);
+
+/* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
+int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPAIR_B200_H */

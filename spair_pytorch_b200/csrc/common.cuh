@@ -1,0 +1,70 @@
+// Shared device helpers for libspair_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spair_b200.h"
+
+#define SPAIR_LAUNCH_CHECK()                       \
+    do {                                           \
+        cudaError_t e__ = cudaGetLastError();      \
+        return e__ == cudaSuccess ? 0 : (int)e__;  \
+    } while (0)
+
+#define SPAIR_REQUIRE(cond)                        \
+    do {                                           \
+        if (!(cond)) return SPAIR_ERR_INVALID;     \
+    } while (0)
+
+namespace spair {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// torch.clamp(x, -10, 10) and the mask its backward applies (inclusive bounds).
+__device__ __forceinline__ float clamp10(float x) { return fminf(fmaxf(x, -10.0f), 10.0f); }
+__device__ __forceinline__ float clamp10_mask(float x) { return (x >= -10.0f && x <= 10.0f) ? 1.0f : 0.0f; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  `red` is shared scratch of
+// at least NV * (blockDim.x / 32) floats.  Deterministic (fixed tree).
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * nwarp + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float s = lane < nwarp ? red[i * nwarp + lane] : 0.0f;
+            v[i] = warp_sum(s);
+        }
+    }
+}
+
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+
+struct NeighbourList {
+    int n;
+    int dh[SPAIR_MAX_NEIGHBOURS];
+    int dw[SPAIR_MAX_NEIGHBOURS];
+};
+
+inline int grid_for(long long work, int block) {
+    long long g = (work + block - 1) / block;
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace spair

@@ -1,0 +1,345 @@
+// G: spatial-transformer glimpse extractor and the generic paste (inverse stn).
+//
+// glimpse = stn(image, z_where, [Gh,Gw], inverse=False) (reference modules.py:216-273): fused
+// affine_grid + bilinear grid_sample, border padding, align_corners=False.
+//
+// Layout / schedule: one CTA per object.  The object's source window (<= 48 px + 1 on a side for
+// model-generated boxes) is staged once per channel into shared memory with 128-bit loads
+// (rows are 16-byte aligned when Iw % 4 == 0); the per-column and per-row sample coordinates
+// are computed once per CTA into shared tables, so the texel loop is 4 LDS + 4 FMA.  Windows
+// that do not fit the tile (only reachable through the generic stn() API) sample global memory
+// directly.  Backward wrt z_where is a per-object reduction (no atomics); the optional image
+// gradient (generic stn() API only — the model's image has no grad) is scattered with atomics.
+#include "warp_math.cuh"
+
+namespace spair {
+
+constexpr int kGlimpseThreads = 256;
+constexpr int kTileW = 72;   // floats, multiple of 4
+constexpr int kTileH = 68;
+
+struct Window {
+    int x_lo, y_lo, tw, th;   // tile origin (x aligned down to 4) and extent
+    bool staged;
+};
+
+// Fills the per-column / per-row coordinate tables (clipped source coordinate and the clip mask
+// of grid_sampler's clip_coordinates_set_grad) and derives the window to stage.
+__device__ __forceinline__ Window glimpse_setup(const FwdAffine& A, int Ih, int Iw, int Gh, int Gw, float* col_ix,
+                                                float* row_iy, float* col_m, float* row_m, bool aligned) {
+    for (int j = threadIdx.x; j < Gw; j += blockDim.x) {
+        float ix = unnormalize(affine_coord(base_coord(j, Gw), A.ax, A.cx), 0.5f * (float)Iw);
+        float m = 1.0f;
+        if (ix <= 0.0f) { ix = 0.0f; m = 0.0f; }
+        else if (ix >= (float)(Iw - 1)) { ix = (float)(Iw - 1); m = 0.0f; }
+        col_ix[j] = ix;
+        if (col_m) col_m[j] = m;
+    }
+    for (int i = threadIdx.x; i < Gh; i += blockDim.x) {
+        float iy = unnormalize(affine_coord(base_coord(i, Gh), A.ay, A.cy), 0.5f * (float)Ih);
+        float m = 1.0f;
+        if (iy <= 0.0f) { iy = 0.0f; m = 0.0f; }
+        else if (iy >= (float)(Ih - 1)) { iy = (float)(Ih - 1); m = 0.0f; }
+        row_iy[i] = iy;
+        if (row_m) row_m[i] = m;
+    }
+    __syncthreads();
+    // coordinates are monotone in j (either direction): the window is spanned by the end points
+    const float xa = col_ix[0], xb = col_ix[Gw - 1], ya = row_iy[0], yb = row_iy[Gh - 1];
+    const int x0 = (int)floorf(fminf(xa, xb)), x1 = min((int)floorf(fmaxf(xa, xb)) + 1, Iw - 1);
+    const int y0 = (int)floorf(fminf(ya, yb)), y1 = min((int)floorf(fmaxf(ya, yb)) + 1, Ih - 1);
+    Window w;
+    w.x_lo = x0 & ~3;
+    w.y_lo = y0;
+    const int x_end = min((x1 + 4) & ~3, Iw);
+    w.tw = x_end - w.x_lo;
+    w.th = y1 - y0 + 1;
+    w.staged = aligned && w.tw <= kTileW && w.th <= kTileH;
+    return w;
+}
+
+__device__ __forceinline__ void stage_window(const float* __restrict__ plane, int Iw, const Window& w,
+                                             float* __restrict__ tile) {
+    const int vec_per_row = w.tw >> 2;
+    const int nvec = vec_per_row * w.th;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const int ry = v / vec_per_row, rx = (v - ry * vec_per_row) << 2;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(plane + (long long)(w.y_lo + ry) * Iw + w.x_lo + rx));
+        *reinterpret_cast<float4*>(tile + ry * w.tw + rx) = q;
+    }
+}
+
+struct Taps {
+    float v00, v01, v10, v11;
+};
+
+__device__ __forceinline__ Taps fetch_taps(const float* __restrict__ plane, int Iw, int Ih, const Window& w,
+                                           const float* __restrict__ tile, int x0, int y0) {
+    Taps t;
+    const bool x1ok = x0 + 1 <= Iw - 1, y1ok = y0 + 1 <= Ih - 1;
+    if (w.staged) {
+        const float* p = tile + (y0 - w.y_lo) * w.tw + (x0 - w.x_lo);
+        t.v00 = p[0];
+        t.v01 = x1ok ? p[1] : 0.0f;
+        t.v10 = y1ok ? p[w.tw] : 0.0f;
+        t.v11 = (x1ok && y1ok) ? p[w.tw + 1] : 0.0f;
+    } else {
+        const float* p = plane + (long long)y0 * Iw + x0;
+        t.v00 = __ldg(p);
+        t.v01 = x1ok ? __ldg(p + 1) : 0.0f;
+        t.v10 = y1ok ? __ldg(p + Iw) : 0.0f;
+        t.v11 = (x1ok && y1ok) ? __ldg(p + Iw + 1) : 0.0f;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(kGlimpseThreads)
+glimpse_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, const int* __restrict__ cells,
+                   int B, int HW, int C, int Ih, int Iw, int Gh, int Gw, float* __restrict__ out, int ld_out,
+                   int aligned) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* col_ix = tile + kTileW * kTileH;
+    float* row_iy = col_ix + Gw;
+    const int r = blockIdx.x;
+    const int b = cells ? r % B : r;
+    const long long o = cells ? (long long)b * HW + cells[r / B] : r;
+    const float4 zw = *reinterpret_cast<const float4*>(z_where + o * 4);
+    const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
+    const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, nullptr, nullptr, aligned != 0);
+    const int GG = Gh * Gw;
+    for (int c = 0; c < C; ++c) {
+        const float* plane = image + ((long long)b * C + c) * Ih * Iw;
+        if (w.staged) {
+            stage_window(plane, Iw, w, tile);
+            __syncthreads();
+        }
+        float* orow = out + (long long)r * ld_out + (long long)c * GG;
+        for (int t = threadIdx.x; t < GG; t += blockDim.x) {
+            const int i = t / Gw, j = t - i * Gw;
+            const float ix = col_ix[j], iy = row_iy[i];
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+            const Taps v = fetch_taps(plane, Iw, Ih, w, tile, (int)fx0, (int)fy0);
+            float acc = __fmul_rn(v.v00, __fmul_rn(wx0, wy0));
+            acc = fmaf(v.v01, __fmul_rn(wx1, wy0), acc);
+            acc = fmaf(v.v10, __fmul_rn(wx0, wy1), acc);
+            acc = fmaf(v.v11, __fmul_rn(wx1, wy1), acc);
+            orow[t] = acc;
+        }
+        if (w.staged) __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kGlimpseThreads)
+glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, const int* __restrict__ cells,
+                   int B, int HW, int C, int Ih, int Iw, int Gh, int Gw, const float* __restrict__ d_out, int ld_out,
+                   float* __restrict__ d_zw, float* __restrict__ d_image, int aligned) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* col_ix = tile + kTileW * kTileH;
+    float* row_iy = col_ix + Gw;
+    float* col_m = row_iy + Gh;
+    float* row_m = col_m + Gw;
+    __shared__ float red[4 * (kGlimpseThreads / 32)];
+    const int r = blockIdx.x;
+    const int b = cells ? r % B : r;
+    const long long o = cells ? (long long)b * HW + cells[r / B] : r;
+    const float4 zw = *reinterpret_cast<const float4*>(z_where + o * 4);
+    const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
+    const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, col_m, row_m, aligned != 0);
+    const int GG = Gh * Gw;
+    // acc[0] = sum dL/dgx, acc[1] = sum dL/dgy, acc[2] = sum dL/dgx * base_x, acc[3] = sum dL/dgy * base_y
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int c = 0; c < C; ++c) {
+        const float* plane = image + ((long long)b * C + c) * Ih * Iw;
+        float* gplane = d_image ? d_image + ((long long)b * C + c) * Ih * Iw : nullptr;
+        if (w.staged) {
+            stage_window(plane, Iw, w, tile);
+            __syncthreads();
+        }
+        const float* grow = d_out + (long long)r * ld_out + (long long)c * GG;
+        for (int t = threadIdx.x; t < GG; t += blockDim.x) {
+            const int i = t / Gw, j = t - i * Gw;
+            const float ix = col_ix[j], iy = row_iy[i];
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            const Taps v = fetch_taps(plane, Iw, Ih, w, tile, x0, y0);
+            const float g = grow[t];
+            // grid_sampler_2d_backward: d out / d ix and d out / d iy
+            const float gix = g * ((v.v01 - v.v00) * wy0 + (v.v11 - v.v10) * wy1);
+            const float giy = g * ((v.v10 - v.v00) * wx0 + (v.v11 - v.v01) * wx1);
+            const float dgx = gix * col_m[j], dgy = giy * row_m[i];
+            acc[0] += dgx;
+            acc[1] += dgy;
+            acc[2] += dgx * base_coord(j, Gw);
+            acc[3] += dgy * base_coord(i, Gh);
+            if (gplane) {
+                const bool x1ok = x0 + 1 <= Iw - 1, y1ok = y0 + 1 <= Ih - 1;
+                float* p = gplane + (long long)y0 * Iw + x0;
+                atomicAdd(p, g * wx0 * wy0);
+                if (x1ok) atomicAdd(p + 1, g * wx1 * wy0);
+                if (y1ok) atomicAdd(p + Iw, g * wx0 * wy1);
+                if (x1ok && y1ok) atomicAdd(p + Iw + 1, g * wx1 * wy1);
+            }
+        }
+        if (w.staged) __syncthreads();
+    }
+    block_sum<4>(acc, red);
+    if (threadIdx.x == 0) {
+        const float hx = 0.5f * (float)Iw, hy = 0.5f * (float)Ih;   // d ix / d gx (unnormalize)
+        // gx = xs * base + (2 xt - 1)
+        d_zw[(long long)r * 4 + 0] = 2.0f * hx * acc[0];
+        d_zw[(long long)r * 4 + 1] = 2.0f * hy * acc[1];
+        d_zw[(long long)r * 4 + 2] = hx * acc[2];
+        d_zw[(long long)r * 4 + 3] = hy * acc[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic paste: stn(image, z_where, [Oh,Ow], inverse=True), zeros padding (modules.py:255-269)
+// ------------------------------------------------------------------------------------------
+__global__ void paste_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, int n, int C,
+                                 int Gh, int Gw, int Oh, int Ow, float* __restrict__ out) {
+    const int obj = blockIdx.y;
+    const float4 zw = *reinterpret_cast<const float4*>(z_where + (long long)obj * 4);
+    const InvAffine A(zw.x, zw.y, zw.z, zw.w);
+    const int npix = Oh * Ow;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int Y = p / Ow, X = p - Y * Ow;
+        const float ix = unnormalize(affine_coord(base_coord(X, Ow), A.ax, A.cx), 0.5f * (float)Gw);
+        const float iy = unnormalize(affine_coord(base_coord(Y, Oh), A.ay, A.cy), 0.5f * (float)Gh);
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const bool inside = fx0 >= -1.0f && fx0 <= (float)(Gw - 1) && fy0 >= -1.0f && fy0 <= (float)(Gh - 1);
+        const int x0 = inside ? (int)fx0 : 0, y0 = inside ? (int)fy0 : 0;
+        const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+        const bool xa = inside && x0 >= 0, xb = inside && x0 + 1 <= Gw - 1, ya = inside && y0 >= 0, yb = inside && y0 + 1 <= Gh - 1;
+        for (int c = 0; c < C; ++c) {
+            const float* pl = image + ((long long)obj * C + c) * Gh * Gw;
+            float acc = 0.0f;
+            if (xa && ya) acc = __fmul_rn(pl[y0 * Gw + x0], __fmul_rn(wx0, wy0));
+            if (xb && ya) acc = fmaf(pl[y0 * Gw + x0 + 1], __fmul_rn(wx1, wy0), acc);
+            if (xa && yb) acc = fmaf(pl[(y0 + 1) * Gw + x0], __fmul_rn(wx0, wy1), acc);
+            if (xb && yb) acc = fmaf(pl[(y0 + 1) * Gw + x0 + 1], __fmul_rn(wx1, wy1), acc);
+            out[((long long)obj * C + c) * npix + p] = acc;
+        }
+    }
+}
+
+__global__ void paste_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, int n, int C,
+                                 int Gh, int Gw, int Oh, int Ow, const float* __restrict__ d_out,
+                                 float* __restrict__ d_image, float* __restrict__ d_zw) {
+    __shared__ float red[4 * 8];
+    const int obj = blockIdx.y;
+    const float4 zw = *reinterpret_cast<const float4*>(z_where + (long long)obj * 4);
+    const InvAffine A(zw.x, zw.y, zw.z, zw.w);
+    const int npix = Oh * Ow;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // sum dgx, sum dgy, sum dgx*bX, sum dgy*bY
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int Y = p / Ow, X = p - Y * Ow;
+        const float bX = base_coord(X, Ow), bY = base_coord(Y, Oh);
+        const float ix = unnormalize(affine_coord(bX, A.ax, A.cx), 0.5f * (float)Gw);
+        const float iy = unnormalize(affine_coord(bY, A.ay, A.cy), 0.5f * (float)Gh);
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const bool inside = fx0 >= -1.0f && fx0 <= (float)(Gw - 1) && fy0 >= -1.0f && fy0 <= (float)(Gh - 1);
+        if (!inside) continue;
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+        const bool xa = x0 >= 0, xb = x0 + 1 <= Gw - 1, ya = y0 >= 0, yb = y0 + 1 <= Gh - 1;
+        float gix = 0.0f, giy = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const long long po = ((long long)obj * C + c) * Gh * Gw;
+            const float* pl = image + po;
+            const float g = d_out[((long long)obj * C + c) * npix + p];
+            const float v00 = (xa && ya) ? pl[y0 * Gw + x0] : 0.0f, v01 = (xb && ya) ? pl[y0 * Gw + x0 + 1] : 0.0f;
+            const float v10 = (xa && yb) ? pl[(y0 + 1) * Gw + x0] : 0.0f, v11 = (xb && yb) ? pl[(y0 + 1) * Gw + x0 + 1] : 0.0f;
+            gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+            giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+            if (d_image) {
+                float* gp = d_image + po;
+                if (xa && ya) atomicAdd(gp + y0 * Gw + x0, g * wx0 * wy0);
+                if (xb && ya) atomicAdd(gp + y0 * Gw + x0 + 1, g * wx1 * wy0);
+                if (xa && yb) atomicAdd(gp + (y0 + 1) * Gw + x0, g * wx0 * wy1);
+                if (xb && yb) atomicAdd(gp + (y0 + 1) * Gw + x0 + 1, g * wx1 * wy1);
+            }
+        }
+        const float dgx = gix * 0.5f * (float)Gw, dgy = giy * 0.5f * (float)Gh;
+        acc[0] += dgx;
+        acc[1] += dgy;
+        acc[2] += dgx * bX;
+        acc[3] += dgy * bY;
+    }
+    block_sum<4>(acc, red);
+    if (threadIdx.x == 0 && d_zw) {
+        // gx = bX * (1/xs) - (2xt-1)/xs
+        const float xtp = 2.0f * zw.x - 1.0f, ytp = 2.0f * zw.y - 1.0f;
+        atomicAdd(d_zw + (long long)obj * 4 + 0, -2.0f * acc[0] / zw.z);
+        atomicAdd(d_zw + (long long)obj * 4 + 1, -2.0f * acc[1] / zw.w);
+        atomicAdd(d_zw + (long long)obj * 4 + 2, (-acc[2] + acc[0] * xtp) / (zw.z * zw.z));
+        atomicAdd(d_zw + (long long)obj * 4 + 3, (-acc[3] + acc[1] * ytp) / (zw.w * zw.w));
+    }
+}
+
+}  // namespace spair
+
+using namespace spair;
+
+static size_t glimpse_smem(int Gh, int Gw, bool bwd) {
+    return sizeof(float) * (size_t)(kTileW * kTileH + (bwd ? 2 : 1) * (Gh + Gw));
+}
+
+extern "C" int spair_glimpse_fwd(const float* image, const float* z_where, const int* cells, int n_cells, int B,
+                                 int HW, int C, int Ih, int Iw, int Gh, int Gw, float* out, int ld_out,
+                                 void* stream) {
+    SPAIR_REQUIRE(image && z_where && out && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
+    SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
+    const int rows = cells ? n_cells * B : B;
+    const size_t smem = glimpse_smem(Gh, Gw, false);
+    SPAIR_REQUIRE(smem <= 200 * 1024);
+    const int aligned = (Iw % 4 == 0) && ((uintptr_t)image % 16 == 0);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(glimpse_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    glimpse_fwd_kernel<<<rows, kGlimpseThreads, smem, (cudaStream_t)stream>>>(image, z_where, cells, B, HW, C, Ih, Iw,
+                                                                              Gh, Gw, out, ld_out, aligned);
+    SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_glimpse_bwd(const float* image, const float* z_where, const int* cells, int n_cells, int B,
+                                 int HW, int C, int Ih, int Iw, int Gh, int Gw, const float* d_out, int ld_out,
+                                 float* d_z_where_local, float* d_image, void* stream) {
+    SPAIR_REQUIRE(image && z_where && d_out && d_z_where_local && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
+    SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
+    const int rows = cells ? n_cells * B : B;
+    const size_t smem = glimpse_smem(Gh, Gw, true);
+    SPAIR_REQUIRE(smem <= 200 * 1024);
+    const int aligned = (Iw % 4 == 0) && ((uintptr_t)image % 16 == 0);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(glimpse_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    glimpse_bwd_kernel<<<rows, kGlimpseThreads, smem, (cudaStream_t)stream>>>(
+        image, z_where, cells, B, HW, C, Ih, Iw, Gh, Gw, d_out, ld_out, d_z_where_local, d_image, aligned);
+    SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_paste_fwd(const float* image, const float* z_where, int n, int C, int Gh, int Gw, int Oh,
+                               int Ow, float* out, void* stream) {
+    SPAIR_REQUIRE(image && z_where && out && n > 0 && C > 0 && Gh > 0 && Gw > 0 && Oh > 0 && Ow > 0);
+    SPAIR_REQUIRE(((uintptr_t)z_where % 16) == 0 && n <= 65535);
+    dim3 grid(grid_for((long long)Oh * Ow, 256), n);
+    paste_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, z_where, n, C, Gh, Gw, Oh, Ow, out);
+    SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_paste_bwd(const float* image, const float* z_where, int n, int C, int Gh, int Gw, int Oh,
+                               int Ow, const float* d_out, float* d_image, float* d_z_where, void* stream) {
+    SPAIR_REQUIRE(image && z_where && d_out && n > 0 && C > 0 && Gh > 0 && Gw > 0 && Oh > 0 && Ow > 0);
+    SPAIR_REQUIRE(((uintptr_t)z_where % 16) == 0 && n <= 65535);
+    if (d_z_where) {
+        cudaError_t e = cudaMemsetAsync(d_z_where, 0, sizeof(float) * 4 * (size_t)n, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid(grid_for((long long)Oh * Ow, 256), n);
+    paste_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, z_where, n, C, Gh, Gw, Oh, Ow, d_out, d_image,
+                                                             d_z_where);
+    SPAIR_LAUNCH_CHECK();
+}

@@ -1,0 +1,299 @@
+"""ctypes binding of libspair_b200.so (the C-ABI declared in include/spair_b200.h).
+
+Every function here is a thin, allocation-free call into one ``extern "C"`` entry point: it
+validates the tensors, passes raw device pointers + the current CUDA stream, and raises on a
+non-zero return code.  There is NO CPU implementation and no alternative backend: if the
+library is missing it is built with nvcc (``_build.py``); if that fails, or a tensor is not a
+CUDA fp32 tensor, the call raises.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import _build
+
+_c_float_p = ctypes.c_void_p
+_LIB = None
+_LOCK = threading.Lock()
+
+
+class BoxGeom(ctypes.Structure):
+    """``spair_box_geom`` of include/spair_b200.h (reference models.py:339-374)."""
+    _fields_ = [(n, ctypes.c_float) for n in
+                ("yx_scale", "yx_min", "hw_scale", "hw_min", "anchor", "img_h", "img_w", "cell_ratio_y", "cell_ratio_x")]
+
+
+class SpairKernelError(RuntimeError):
+    pass
+
+
+_P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_SIGNATURES = {
+    "spair_abi_version": [],
+    "spair_context_gather_fwd": [_P] * 6 + [_P, _I, _P, _I] + [_I] * 5 + [_P, _I, _P, _I, _P, _I, _P],
+    "spair_context_grad_gather": [_P, _I, _P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "spair_box_head_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _I, _P],
+    "spair_box_head_bwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P,
+                           _I, _P, _P],
+    "spair_normal_head_fwd": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _I, _P],
+    "spair_normal_head_bwd": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I,
+                              _P, _I, _P, _P],
+    "spair_pres_head_fwd": [_P, _I, _P, _P, _I, _I, _I, _P, _P],
+    "spair_pres_head_bwd": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P],
+    "spair_glimpse_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    "spair_glimpse_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P],
+    "spair_paste_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "spair_paste_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "spair_render_num_tiles": [_I, _I, _I],
+    "spair_render_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P],
+    "spair_render_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spair_kl_fwd": [_P] * 6 + [_I, _I, _I, _P, _P, _P, _P],
+    "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
+    "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Loads (building first if stale or missing) the kernel library.  Raises if unavailable."""
+    global _LIB
+    if _LIB is None:
+        with _LOCK:
+            if _LIB is None:
+                path = _build.LIB_PATH
+                if _build.is_stale():
+                    try:
+                        path = _build.build()
+                    except Exception as e:  # keep a prebuilt library if nvcc is absent on this box
+                        if not os.path.exists(path):
+                            raise SpairKernelError("libspair_b200.so is missing and could not be built: %s" % e) from e
+                handle = ctypes.CDLL(path)
+                for name, argtypes in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.argtypes = argtypes
+                    fn.restype = ctypes.c_int
+                if handle.spair_abi_version() != 1:
+                    raise SpairKernelError("libspair_b200.so ABI version mismatch")
+                _LIB = handle
+    return _LIB
+
+
+def require_cuda(t, what="input"):
+    """The product path has no CPU implementation: refuse anything that is not a CUDA tensor."""
+    if not t.is_cuda:
+        raise SpairKernelError("%s must be a CUDA tensor: the SPAIR per-cell pipeline runs on sm_100a kernels and "
+                               "has no CPU implementation" % what)
+
+
+def _check(code: int, name: str) -> None:
+    if code != 0:
+        if code < 0:
+            raise SpairKernelError("%s rejected its arguments (SPAIR_ERR_INVALID)" % name)
+        raise SpairKernelError("%s failed: CUDA error %d" % (name, code))
+
+
+def _ptr(t, name="tensor"):
+    """Device pointer of a CUDA fp32 tensor (None -> NULL).  No CPU path exists."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SpairKernelError("%s must live on a CUDA device: the SPAIR kernels have no CPU implementation" % name)
+    if t.dtype != torch.float32:
+        raise SpairKernelError("%s must be float32, got %s" % (name, t.dtype))
+    return t.data_ptr()
+
+
+def _iptr(t, name="index tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous():
+        raise SpairKernelError("%s must be a contiguous CUDA int32 tensor" % name)
+    return t.data_ptr()
+
+
+def _ld(t):
+    """Row stride (leading dimension) of a 2-D view whose rows are contiguous."""
+    if t is None:
+        return 0
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise SpairKernelError("expected a 2-D tensor with unit column stride, got shape %s stride %s"
+                               % (tuple(t.shape), t.stride()))
+    return t.stride(0)
+
+
+def _contig(t, name):
+    if t is not None and not t.is_contiguous():
+        raise SpairKernelError("%s must be contiguous" % name)
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _offsets_array(offsets):
+    flat = [int(v) for pair in offsets for v in pair]
+    return (ctypes.c_int * len(flat))(*flat), len(offsets)
+
+
+# ----------------------------------------------------------------------------------------
+# L0 context
+# ----------------------------------------------------------------------------------------
+def context_gather_fwd(feat, box, attr, depth, pres, edge, cells, offsets, dsts):
+    """feat [B,F,Hc,Wc]; box/attr/depth/pres image-major; cells int32 [n]; dsts: up to three 2-D row views."""
+    B, F, Hc, Wc = feat.shape
+    A = attr.shape[-1]
+    arr, n_nb = _offsets_array(offsets)
+    d = list(dsts) + [None] * (3 - len(dsts))
+    for t in (feat, box, attr, depth, pres, edge):
+        _contig(t, "context input")
+    _check(lib().spair_context_gather_fwd(_ptr(feat), _ptr(box), _ptr(attr), _ptr(depth), _ptr(pres), _ptr(edge),
+                                          _iptr(cells), cells.numel(), arr, n_nb, B, F, Hc, Wc, A,
+                                          _ptr(d[0]), _ld(d[0]), _ptr(d[1]), _ld(d[1]), _ptr(d[2]), _ld(d[2]), _stream()),
+           "spair_context_gather_fwd")
+
+
+def context_grad_gather(dxs, col0, cells, wf_pos, offsets, B, Hc, Wc, A, out):
+    arr, n_nb = _offsets_array(offsets)
+    d = list(dxs) + [None] * (3 - len(dxs))
+    _check(lib().spair_context_grad_gather(_ptr(d[0]), _ld(d[0]), _ptr(d[1]), _ld(d[1]), _ptr(d[2]), _ld(d[2]), col0,
+                                           _iptr(cells), cells.numel(), _iptr(wf_pos), arr, n_nb, B, Hc, Wc, A,
+                                           _ptr(out), _ld(out), _stream()), "spair_context_grad_gather")
+
+
+# ----------------------------------------------------------------------------------------
+# heads
+# ----------------------------------------------------------------------------------------
+def box_head_fwd(y, eps, cells, B, HW, Wc, geom, box, z_where, dmean, dstd, xdsts, n_pt, pt_dst):
+    x = list(xdsts) + [None] * (2 - len(xdsts))
+    _check(lib().spair_box_head_fwd(_ptr(y), _ld(y), _ptr(_contig(eps, "eps")), _iptr(cells), cells.numel(), B, HW, Wc,
+                                    ctypes.byref(geom), _ptr(_contig(box, "box")), _ptr(_contig(z_where, "z_where")),
+                                    _ptr(dmean), _ptr(dstd), dmean.shape[-1],
+                                    _ptr(x[0]), _ld(x[0]), _ptr(x[1]), _ld(x[1]), n_pt, _ptr(pt_dst), _ld(pt_dst),
+                                    _stream()), "spair_box_head_fwd")
+
+
+def box_head_bwd(y, eps, cells, B, HW, Wc, geom, wheel, d_boxes, d_zw_local, d_zw_img, d_dmean, d_dstd, ld_dist,
+                 n_pt, d_pt_src, d_y):
+    d = list(d_boxes) + [None] * (3 - len(d_boxes))
+    _check(lib().spair_box_head_bwd(_ptr(y), _ld(y), _ptr(eps), _iptr(cells), cells.numel(), B, HW, Wc,
+                                    ctypes.byref(geom), _ptr(wheel), _ptr(d[0]), _ld(d[0]), _ptr(d[1]), _ld(d[1]),
+                                    _ptr(d[2]), _ld(d[2]), _ptr(d_zw_local), _ld(d_zw_local), _ptr(d_zw_img),
+                                    _ptr(d_dmean), _ptr(d_dstd), ld_dist, n_pt, _ptr(d_pt_src), _ld(d_pt_src),
+                                    _ptr(d_y), _stream()), "spair_box_head_bwd")
+
+
+def normal_head_fwd(y, W, eps, cells, B, HW, squash, scale, out, dmean_ptr_view, dstd_ptr_view, ld_dist, xdsts, n_pt,
+                    pt_dst):
+    """dmean_ptr_view / dstd_ptr_view: views of the [B,HW,D] maps starting at this head's first column."""
+    x = list(xdsts) + [None] * (2 - len(xdsts))
+    _check(lib().spair_normal_head_fwd(_ptr(y), _ld(y), W, _ptr(_contig(eps, "eps")), _iptr(cells), cells.numel(), B, HW,
+                                       int(squash), float(scale), _ptr(_contig(out, "out")), _ptr(dmean_ptr_view),
+                                       _ptr(dstd_ptr_view), ld_dist, _ptr(x[0]), _ld(x[0]), _ptr(x[1]), _ld(x[1]),
+                                       n_pt, _ptr(pt_dst), _ld(pt_dst), _stream()), "spair_normal_head_fwd")
+
+
+def normal_head_bwd(y, W, eps, cells, B, HW, squash, scale, wheel, d_outs, d_out_img, d_dmean_view, d_dstd_view,
+                    ld_dist, n_pt, d_pt_src, d_y):
+    d = list(d_outs) + [None] * (3 - len(d_outs))
+    _check(lib().spair_normal_head_bwd(_ptr(y), _ld(y), W, _ptr(eps), _iptr(cells), cells.numel(), B, HW, int(squash),
+                                       float(scale), _ptr(wheel), _ptr(d[0]), _ld(d[0]), _ptr(d[1]), _ld(d[1]),
+                                       _ptr(d[2]), _ld(d[2]), _ptr(d_out_img), _ptr(d_dmean_view), _ptr(d_dstd_view),
+                                       ld_dist, n_pt, _ptr(d_pt_src), _ld(d_pt_src), _ptr(d_y), _stream()),
+           "spair_normal_head_bwd")
+
+
+def pres_head_fwd(y, u, cells, B, HW, pres):
+    _check(lib().spair_pres_head_fwd(_ptr(y), _ld(y), _ptr(_contig(u, "u")), _iptr(cells), cells.numel(), B, HW,
+                                     _ptr(_contig(pres, "pres")), _stream()), "spair_pres_head_fwd")
+
+
+def pres_head_bwd(y, u, cells, B, HW, wheel, d_local, d_img, d_y):
+    _check(lib().spair_pres_head_bwd(_ptr(y), _ld(y), _ptr(u), _iptr(cells), cells.numel(), B, HW, _ptr(wheel),
+                                     _ptr(d_local), _ld(d_local), _ptr(d_img), _ptr(d_y), _stream()),
+           "spair_pres_head_bwd")
+
+
+def relu_bwd(dh, h):
+    _check(lib().spair_relu_bwd(_ptr(dh), _ld(dh), _ptr(h), _ld(h), dh.shape[0], dh.shape[1], _stream()),
+           "spair_relu_bwd")
+
+
+# ----------------------------------------------------------------------------------------
+# G glimpse / paste
+# ----------------------------------------------------------------------------------------
+def glimpse_fwd(image, z_where, cells, B, HW, Gh, Gw, out):
+    """cells None: row r samples image r with z_where[r] (plain stn); else wavefront rows."""
+    _, C, Ih, Iw = image.shape
+    _check(lib().spair_glimpse_fwd(_ptr(_contig(image, "image")), _ptr(_contig(z_where, "z_where")), _iptr(cells),
+                                   0 if cells is None else cells.numel(), B, HW, C, Ih, Iw, Gh, Gw, _ptr(out), _ld(out),
+                                   _stream()), "spair_glimpse_fwd")
+
+
+def glimpse_bwd(image, z_where, cells, B, HW, Gh, Gw, d_out, d_zw_local, d_image=None):
+    _, C, Ih, Iw = image.shape
+    _check(lib().spair_glimpse_bwd(_ptr(_contig(image, "image")), _ptr(_contig(z_where, "z_where")), _iptr(cells),
+                                   0 if cells is None else cells.numel(), B, HW, C, Ih, Iw, Gh, Gw, _ptr(d_out),
+                                   _ld(d_out), _ptr(_contig(d_zw_local, "d_zw")), _ptr(_contig(d_image, "d_image")),
+                                   _stream()), "spair_glimpse_bwd")
+
+
+def paste_fwd(image, z_where, Oh, Ow, out):
+    n, C, Gh, Gw = image.shape
+    _check(lib().spair_paste_fwd(_ptr(_contig(image, "image")), _ptr(_contig(z_where, "z_where")), n, C, Gh, Gw, Oh, Ow,
+                                 _ptr(_contig(out, "out")), _stream()), "spair_paste_fwd")
+
+
+def paste_bwd(image, z_where, Oh, Ow, d_out, d_image, d_z_where):
+    n, C, Gh, Gw = image.shape
+    _check(lib().spair_paste_bwd(_ptr(_contig(image, "image")), _ptr(_contig(z_where, "z_where")), n, C, Gh, Gw, Oh, Ow,
+                                 _ptr(_contig(d_out, "d_out")), _ptr(_contig(d_image, "d_image")),
+                                 _ptr(_contig(d_z_where, "d_z_where")), _stream()), "spair_paste_bwd")
+
+
+# ----------------------------------------------------------------------------------------
+# R render
+# ----------------------------------------------------------------------------------------
+def render_num_tiles(B, Ih, Iw):
+    return lib().spair_render_num_tiles(B, Ih, Iw)
+
+
+def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, bce_partial):
+    _check(lib().spair_render_fwd(_ptr(_contig(logits, "logits")), _ptr(_contig(z_where, "z_where")),
+                                  _ptr(_contig(z_depth, "z_depth")), _ptr(_contig(z_pres, "z_pres")), B, HW, C, G, Ih, Iw,
+                                  float(scales[0]), float(scales[1]), float(scales[2]), _ptr(_contig(recon, "recon")),
+                                  _ptr(_contig(denom, "denom")), _ptr(_contig(target, "target")),
+                                  _ptr(_contig(bce_partial, "bce_partial")), _stream()), "spair_render_fwd")
+
+
+def render_bwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, d_recon, target, bce_scale,
+               gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres):
+    _check(lib().spair_render_bwd(_ptr(_contig(logits, "logits")), _ptr(_contig(z_where, "z_where")),
+                                  _ptr(_contig(z_depth, "z_depth")), _ptr(_contig(z_pres, "z_pres")), B, HW, C, G, Ih, Iw,
+                                  float(scales[0]), float(scales[1]), float(scales[2]), _ptr(recon), _ptr(denom),
+                                  _ptr(_contig(d_recon, "d_recon")), _ptr(_contig(target, "target")), _ptr(bce_scale),
+                                  _ptr(gs_ws), _ptr(_contig(d_logits, "d_logits")), _ptr(_contig(d_z_where, "d_z_where")),
+                                  _ptr(_contig(d_z_depth, "d_z_depth")), _ptr(_contig(d_z_pres, "d_z_pres")), _stream()),
+           "spair_render_bwd")
+
+
+# ----------------------------------------------------------------------------------------
+# K KL
+# ----------------------------------------------------------------------------------------
+def kl_fwd(dmean, dstd, pres, prior_mean, prior_std, count_dist0, B, HW, A, kl_map, p_z, kl_sums):
+    for t in (dmean, dstd, pres, prior_mean, prior_std, count_dist0, kl_map, p_z, kl_sums):
+        _contig(t, "kl tensor")
+    _check(lib().spair_kl_fwd(_ptr(dmean), _ptr(dstd), _ptr(pres), _ptr(prior_mean), _ptr(prior_std), _ptr(count_dist0),
+                              B, HW, A, _ptr(kl_map), _ptr(p_z), _ptr(kl_sums), _stream()), "spair_kl_fwd")
+
+
+def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW, A, d_dmean, d_dstd, d_pres):
+    for t in (dmean, dstd, pres, prior_mean, prior_std, p_z, d_sums, d_dmean, d_dstd, d_pres):
+        _contig(t, "kl tensor")
+    _check(lib().spair_kl_bwd(_ptr(dmean), _ptr(dstd), _ptr(pres), _ptr(prior_mean), _ptr(prior_std), _ptr(kl_map),
+                              _ptr(p_z), _ptr(d_sums), B, HW, A, _ptr(d_dmean), _ptr(d_dstd), _ptr(d_pres), _stream()),
+           "spair_kl_bwd")

@@ -1,0 +1,394 @@
+"""Autograd wrappers and the wavefront sweep over the sm_100a kernels (host orchestration).
+
+Nothing here computes on the CPU: every numerical step is either a call into
+``libspair_b200.so`` (``kernels.py``) or a cuBLAS GEMM issued through ``torch.mm/addmm`` on
+preallocated device buffers.  The backward passes are written out by hand instead of taped:
+
+  * ``GlimpseFunction`` / ``PasteFunction`` — ``stn()`` both directions (reference modules.py:216-273);
+  * ``RenderFunction``  — fused decode + inverse warp + compositing (+ BCE) (models.py:481-547);
+  * ``KLFunction``      — masked Normal KLs + count-prior scan (models.py:169-262);
+  * ``CellSweepFunction`` — the whole autoregressive cell loop (models.py:68-117) as Wc+2(Hc-1)
+    wavefronts.  Activations of all cells live in wavefront-major row buffers
+    ``[HW*B, width]`` so every per-wavefront GEMM works on a contiguous row slice, the heads write
+    their results straight into the next network's input columns, and the weight gradients are
+    13 large GEMMs over ALL rows at the end of backward instead of 121 x 13 small ones.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .schedule import WavefrontSchedule
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.contiguous()
+
+
+# ==========================================================================================
+# stn: glimpse (forward direction) and paste (inverse direction)
+# ==========================================================================================
+class GlimpseFunction(torch.autograd.Function):
+    """``stn(image, z_where, [Gh, Gw])``: image [n,C,Ih,Iw], z_where [n,4] -> [n,C,Gh,Gw]."""
+
+    @staticmethod
+    def forward(ctx, image, z_where, Gh, Gw):
+        image, z_where = _c(image), _c(z_where)
+        n, C = image.shape[0], image.shape[1]
+        out = torch.empty(n, C * Gh * Gw, device=image.device, dtype=torch.float32)
+        K.glimpse_fwd(image, z_where, None, n, 1, Gh, Gw, out)
+        ctx.save_for_backward(image, z_where)
+        ctx.dims = (Gh, Gw)
+        return out.view(n, C, Gh, Gw)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        image, z_where = ctx.saved_tensors
+        Gh, Gw = ctx.dims
+        n = image.shape[0]
+        d_zw = torch.empty(n, 4, device=image.device, dtype=torch.float32)
+        d_image = torch.zeros_like(image) if ctx.needs_input_grad[0] else None
+        K.glimpse_bwd(image, z_where, None, n, 1, Gh, Gw, _c(d_out).view(n, -1), d_zw, d_image)
+        return d_image, d_zw, None, None
+
+
+class PasteFunction(torch.autograd.Function):
+    """``stn(image, z_where, [Oh, Ow], inverse=True)``: image [n,C,Gh,Gw] -> [n,C,Oh,Ow]."""
+
+    @staticmethod
+    def forward(ctx, image, z_where, Oh, Ow):
+        image, z_where = _c(image), _c(z_where)
+        n, C = image.shape[0], image.shape[1]
+        out = torch.empty(n, C, Oh, Ow, device=image.device, dtype=torch.float32)
+        K.paste_fwd(image, z_where, Oh, Ow, out)
+        ctx.save_for_backward(image, z_where)
+        ctx.dims = (Oh, Ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        image, z_where = ctx.saved_tensors
+        Oh, Ow = ctx.dims
+        d_zw = torch.empty(image.shape[0], 4, device=image.device, dtype=torch.float32)
+        d_image = torch.zeros_like(image)
+        K.paste_bwd(image, z_where, Oh, Ow, _c(d_out), d_image, d_zw)
+        return d_image, d_zw, None, None
+
+
+# ==========================================================================================
+# renderer
+# ==========================================================================================
+class RenderFunction(torch.autograd.Function):
+    """(logits [N,G,G,C+1], z_where [N,4], z_depth [N], z_pres [N], target [B,C,Ih,Iw] | None)
+    -> (recon [B,C,Ih,Iw], bce_sum scalar).  N = B*HW, objects of one image contiguous."""
+
+    @staticmethod
+    def forward(ctx, logits, z_where, z_depth, z_pres, target, B, HW, C, G, Ih, Iw, scales):
+        logits, z_where, z_depth, z_pres = _c(logits), _c(z_where), _c(z_depth), _c(z_pres)
+        dev = logits.device
+        recon = torch.empty(B, C, Ih, Iw, device=dev, dtype=torch.float32)
+        denom = torch.empty(B, Ih, Iw, device=dev, dtype=torch.float32)
+        partial = None
+        if target is not None:
+            target = _c(target)
+            partial = torch.empty(K.render_num_tiles(B, Ih, Iw), device=dev, dtype=torch.float32)
+        K.render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, partial)
+        bce = partial.sum() if partial is not None else torch.zeros((), device=dev)
+        ctx.save_for_backward(logits, z_where, z_depth, z_pres, recon, denom, target)
+        ctx.meta = (B, HW, C, G, Ih, Iw, scales)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(denom)
+        return recon, bce, denom
+
+    @staticmethod
+    def backward(ctx, d_recon, d_bce, _d_denom):
+        logits, z_where, z_depth, z_pres, recon, denom, target = ctx.saved_tensors
+        B, HW, C, G, Ih, Iw, scales = ctx.meta
+        dev = logits.device
+        if d_bce is None and d_recon is None:
+            return (None,) * 12
+        use_target = target if d_bce is not None else None
+        bce_scale = _c(d_bce.reshape(1).float()) if d_bce is not None else None
+        gs = torch.empty(B, C + 1, Ih, Iw, device=dev, dtype=torch.float32)
+        d_logits = torch.empty_like(logits)
+        d_zw = torch.empty_like(z_where)
+        d_depth = torch.empty_like(z_depth)
+        d_pres = torch.empty_like(z_pres)
+        K.render_bwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, _c(d_recon), use_target,
+                     bce_scale, gs, d_logits, d_zw, d_depth, d_pres)
+        return (d_logits, d_zw, d_depth, d_pres) + (None,) * 8
+
+
+# ==========================================================================================
+# KL
+# ==========================================================================================
+class KLFunction(torch.autograd.Function):
+    """(dmean, dstd [B,HW,D], pres [B,HW]) -> kl_sums [B,7] (cy, cx, height, width, attr, depth, pres)
+    plus the non-differentiable kl_map [B,HW,D+1] for inspection."""
+
+    @staticmethod
+    def forward(ctx, dmean, dstd, pres, prior_mean, prior_std, count_dist0, A):
+        dmean, dstd, pres = _c(dmean), _c(dstd), _c(pres)
+        B, HW, D = dmean.shape
+        dev = dmean.device
+        kl_map = torch.empty(B, HW, D + 1, device=dev, dtype=torch.float32)
+        p_z = torch.empty(B, HW, device=dev, dtype=torch.float32)
+        sums = torch.empty(B, 7, device=dev, dtype=torch.float32)
+        K.kl_fwd(dmean, dstd, pres, prior_mean, prior_std, count_dist0, B, HW, A, kl_map, p_z, sums)
+        ctx.save_for_backward(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z)
+        ctx.A = A
+        ctx.mark_non_differentiable(kl_map)
+        return sums, kl_map
+
+    @staticmethod
+    def backward(ctx, d_sums, _d_map):
+        dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z = ctx.saved_tensors
+        B, HW, _ = dmean.shape
+        d_dmean, d_dstd, d_pres = torch.empty_like(dmean), torch.empty_like(dstd), torch.empty_like(pres)
+        K.kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, _c(d_sums), B, HW, ctx.A, d_dmean, d_dstd, d_pres)
+        return d_dmean, d_dstd, d_pres, None, None, None, None
+
+
+# ==========================================================================================
+# the autoregressive cell sweep
+# ==========================================================================================
+@dataclass
+class SweepPlan:
+    """Static description of one model's sweep (built once per model / device)."""
+    schedule: WavefrontSchedule
+    geom: "K.BoxGeom"
+    B_hint: int
+    F: int                 # backbone features
+    A: int                 # attribute dims
+    P: int                 # passthrough features
+    C: int
+    Ih: int
+    Iw: int
+    G: int
+    order_dev: torch.Tensor = None     # int32 [HW] cells in wavefront-major order
+    wf_pos_dev: torch.Tensor = None    # int32 [HW]
+    missing_dev: torch.Tensor = None   # float [HW, n_nb] by position
+    gather_index: torch.Tensor = None  # int64 [HW] wf_pos as gather index
+    n_hidden: dict = field(default_factory=dict)
+
+    @property
+    def E(self):
+        return self.A + 6
+
+    @property
+    def ctx_dim(self):
+        return len(self.schedule.offsets) * self.E
+
+    def to(self, device):
+        s = self.schedule
+        self.order_dev = torch.from_numpy(np.ascontiguousarray(s.order)).to(device=device, dtype=torch.int32)
+        self.wf_pos_dev = torch.from_numpy(np.ascontiguousarray(s.wf_pos)).to(device=device, dtype=torch.int32)
+        self.missing_dev = torch.from_numpy(s.missing.astype(np.float32)).to(device)
+        self.gather_index = self.wf_pos_dev.long()
+        return self
+
+
+class _ManualMLP:
+    """cuBLAS MLP over row slices of preallocated buffers, with a hand-written backward.
+    ``weights``/``biases``: hidden layers then ONE output layer (multi-head networks pass the
+    concatenation of their heads)."""
+
+    def __init__(self, weights: List[torch.Tensor], biases: List[torch.Tensor], rows: int, device):
+        self.W, self.b = weights, biases
+        self.widths = [w.shape[0] for w in weights]
+        self.n_in = weights[0].shape[1]
+        self.X = torch.empty(rows, self.n_in, device=device, dtype=torch.float32)
+        self.H = [torch.empty(rows, w, device=device, dtype=torch.float32) for w in self.widths[:-1]]
+        self.Y = torch.empty(rows, self.widths[-1], device=device, dtype=torch.float32)
+        self.dX = self.dH = self.dY = None
+
+    def forward(self, r0, r1):
+        inp = self.X[r0:r1]
+        for l, h in enumerate(self.H):
+            torch.addmm(self.b[l], inp, self.W[l].t(), out=h[r0:r1])
+            torch.relu_(h[r0:r1])
+            inp = h[r0:r1]
+        torch.addmm(self.b[-1], inp, self.W[-1].t(), out=self.Y[r0:r1])
+
+    def alloc_grads(self):
+        self.dX = torch.empty_like(self.X)
+        self.dH = [torch.empty_like(h) for h in self.H]
+        self.dY = torch.empty_like(self.Y)
+
+    def backward_dx(self, r0, r1):
+        g = self.dY[r0:r1]
+        for l in range(len(self.H) - 1, -1, -1):
+            torch.mm(g, self.W[l + 1], out=self.dH[l][r0:r1])
+            K.relu_bwd(self.dH[l][r0:r1], self.H[l][r0:r1])
+            g = self.dH[l][r0:r1]
+        torch.mm(g, self.W[0], out=self.dX[r0:r1])
+
+    def weight_grads(self):
+        """One GEMM per layer over all rows: dW = dY^T X, db = column sums."""
+        inputs = [self.X] + self.H
+        grads = self.dH + [self.dY]
+        return [g.t().mm(i) for g, i in zip(grads, inputs)], [g.sum(0) for g in grads]
+
+
+class CellSweepFunction(torch.autograd.Function):
+    """forward(plan, x, feat, edge, eps_where, eps_attr, eps_depth, u_pres, wheel, *params)
+    -> (z_where [B,HW,4], attr [B,HW,A], depth [B,HW], pres [B,HW], dmean [B,HW,D], dstd [B,HW,D], box [B,HW,4])
+
+    ``params`` order: box_network (hidden W,b..., head0 W,b, head1 W,b), object_encoder (hidden..., out),
+    z_network (hidden..., head0, head1), obj_network (hidden..., out)."""
+
+    @staticmethod
+    def forward(ctx, plan: SweepPlan, x, feat, edge, eps_where, eps_attr, eps_depth, u_pres, wheel, *params):
+        s = plan.schedule
+        dev = feat.device
+        B = feat.shape[0]
+        HW = s.Hc * s.Wc
+        A, P, F, E, CTX, G = plan.A, plan.P, plan.F, plan.E, plan.ctx_dim, plan.G
+        D = 4 + A + 1
+        rows = HW * B
+        x, feat, edge = _c(x.detach()), _c(feat.detach()), _c(edge.detach())
+        params = [p.detach() for p in params]
+
+        nh = plan.n_hidden
+        it = iter(params)
+
+        def take(n_hidden, n_heads):
+            Ws, bs = [], []
+            for _ in range(n_hidden):
+                Ws.append(next(it)); bs.append(next(it))
+            hw_, hb_ = [], []
+            for _ in range(n_heads):
+                hw_.append(next(it)); hb_.append(next(it))
+            Ws.append(torch.cat(hw_, 0) if n_heads > 1 else hw_[0])
+            bs.append(torch.cat(hb_, 0) if n_heads > 1 else hb_[0])
+            return Ws, bs
+
+        box_mlp = _ManualMLP(*take(nh["box"], 2), rows, dev)
+        enc_mlp = _ManualMLP(*take(nh["enc"], 1), rows, dev)
+        z_mlp = _ManualMLP(*take(nh["z"], 2), rows, dev)
+        obj_mlp = _ManualMLP(*take(nh["obj"], 1), rows, dev)
+        assert box_mlp.n_in == F + CTX and z_mlp.n_in == F + CTX + P + 4 + A and obj_mlp.n_in == z_mlp.n_in + 1
+        assert enc_mlp.n_in == plan.C * G * G
+
+        box = torch.empty(B, HW, 4, device=dev)
+        z_where = torch.empty(B, HW, 4, device=dev)
+        attr = torch.empty(B, HW, A, device=dev)
+        depth = torch.empty(B, HW, device=dev)
+        pres = torch.empty(B, HW, device=dev)
+        dmean = torch.empty(B, HW, D, device=dev)
+        dstd = torch.empty(B, HW, D, device=dev)
+        c_pt, c_box, c_attr, c_depth = F + CTX, F + CTX + P, F + CTX + P + 4, F + CTX + P + 4 + A
+
+        for t in range(s.n_wavefronts):
+            c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
+            r0, r1 = c0 * B, c1 * B
+            cells = plan.order_dev[c0:c1]
+            Xb, Xz, Xo = box_mlp.X[r0:r1], z_mlp.X[r0:r1], obj_mlp.X[r0:r1]
+            K.context_gather_fwd(feat, box, attr, depth, pres, edge, cells, s.offsets, (Xb, Xz, Xo))
+            box_mlp.forward(r0, r1)
+            K.box_head_fwd(box_mlp.Y[r0:r1], eps_where, cells, B, HW, s.Wc, plan.geom, box, z_where, dmean, dstd,
+                           (Xz[:, c_box:], Xo[:, c_box:]), P, Xz[:, c_pt:])
+            K.glimpse_fwd(x, z_where, cells, B, HW, G, G, enc_mlp.X[r0:r1])
+            enc_mlp.forward(r0, r1)
+            K.normal_head_fwd(enc_mlp.Y[r0:r1], A, eps_attr, cells, B, HW, 0, 1.0, attr, dmean[..., 4:], dstd[..., 4:], D,
+                              (Xz[:, c_attr:], Xo[:, c_attr:]), 0, None)
+            z_mlp.forward(r0, r1)
+            K.normal_head_fwd(z_mlp.Y[r0:r1], 1, eps_depth, cells, B, HW, 1, 4.0, depth, dmean[..., D - 1:],
+                              dstd[..., D - 1:], D, (Xo[:, c_depth:],), P, Xo[:, c_pt:])
+            obj_mlp.forward(r0, r1)
+            K.pres_head_fwd(obj_mlp.Y[r0:r1], u_pres, cells, B, HW, pres)
+
+        ctx.plan = plan
+        ctx.mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
+        ctx.noise = (eps_where, eps_attr, eps_depth, u_pres, wheel)
+        ctx.x = x
+        ctx.n_params = len(params)
+        ctx.save_for_backward(z_where)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(box)
+        return z_where, attr, depth, pres, dmean, dstd, box
+
+    @staticmethod
+    def backward(ctx, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd, _d_box):
+        plan: SweepPlan = ctx.plan
+        s = plan.schedule
+        (z_where,) = ctx.saved_tensors
+        box_mlp, enc_mlp, z_mlp, obj_mlp = ctx.mlps
+        eps_where, eps_attr, eps_depth, u_pres, wheel = ctx.noise
+        x = ctx.x
+        dev = z_where.device
+        B = z_where.shape[0]
+        HW = s.Hc * s.Wc
+        A, P, F, E, CTX, G = plan.A, plan.P, plan.F, plan.E, plan.ctx_dim, plan.G
+        D = 4 + A + 1
+        d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd = (_c(t) for t in (d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd))
+        if (d_dmean is None) != (d_dstd is None):
+            d_dmean = torch.zeros(B, HW, D, device=dev) if d_dmean is None else d_dmean
+            d_dstd = torch.zeros(B, HW, D, device=dev) if d_dstd is None else d_dstd
+        for m in (box_mlp, enc_mlp, z_mlp, obj_mlp):
+            m.alloc_grads()
+        n_max = s.max_cells * B
+        d_cell = torch.empty(n_max, E, device=dev)
+        d_zw_local = torch.empty(n_max, 4, device=dev)
+        c_pt, c_box, c_attr, c_depth = F + CTX, F + CTX + P, F + CTX + P + 4, F + CTX + P + 4 + A
+        dm_attr = None if d_dmean is None else d_dmean[..., 4:]
+        ds_attr = None if d_dstd is None else d_dstd[..., 4:]
+        dm_depth = None if d_dmean is None else d_dmean[..., D - 1:]
+        ds_depth = None if d_dstd is None else d_dstd[..., D - 1:]
+
+        for t in range(s.n_wavefronts - 1, -1, -1):
+            c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
+            r0, r1 = c0 * B, c1 * B
+            n = r1 - r0
+            cells = plan.order_dev[c0:c1]
+            dXz, dXo = z_mlp.dX[r0:r1], obj_mlp.dX[r0:r1]
+            dc = d_cell[:n]
+            # gradient arriving through the lateral context of later cells (models.py:106 -> 73)
+            K.context_grad_gather((box_mlp.dX, z_mlp.dX, obj_mlp.dX), F, cells, plan.wf_pos_dev, s.offsets, B, s.Hc, s.Wc,
+                                  A, dc)
+            # z_pres
+            K.pres_head_bwd(obj_mlp.Y[r0:r1], u_pres, cells, B, HW, wheel, dc[:, E - 1:], d_pres, obj_mlp.dY[r0:r1])
+            obj_mlp.backward_dx(r0, r1)
+            # z_depth
+            K.normal_head_bwd(z_mlp.Y[r0:r1], 1, eps_depth, cells, B, HW, 1, 4.0, wheel,
+                              (dXo[:, c_depth:], dc[:, E - 2:E - 1]), d_depth, dm_depth, ds_depth, D,
+                              P, dXo[:, c_pt:], z_mlp.dY[r0:r1])
+            z_mlp.backward_dx(r0, r1)
+            # z_what
+            K.normal_head_bwd(enc_mlp.Y[r0:r1], A, eps_attr, cells, B, HW, 0, 1.0, None,
+                              (dXz[:, c_attr:], dXo[:, c_attr:], dc[:, 4:4 + A]), d_attr, dm_attr, ds_attr, D,
+                              0, None, enc_mlp.dY[r0:r1])
+            enc_mlp.backward_dx(r0, r1)
+            K.glimpse_bwd(x, z_where, cells, B, HW, G, G, enc_mlp.dX[r0:r1], d_zw_local[:n], None)
+            # z_where
+            K.box_head_bwd(box_mlp.Y[r0:r1], eps_where, cells, B, HW, s.Wc, plan.geom, wheel,
+                           (dXz[:, c_box:], dXo[:, c_box:], dc[:, 0:4]), d_zw_local[:n], d_zw, d_dmean, d_dstd, D,
+                           P, dXz[:, c_pt:], box_mlp.dY[r0:r1])
+            box_mlp.backward_dx(r0, r1)
+
+        # ---- gradients of shared inputs, accumulated over all rows at once ----
+        d_in = box_mlp.dX[:, :F + CTX] + z_mlp.dX[:, :F + CTX] + obj_mlp.dX[:, :F + CTX]     # [rows, F+CTX]
+        d_in = d_in.view(HW, B, F + CTX)
+        # backbone features: wavefront-major rows -> [B,F,Hc,Wc]
+        d_feat = d_in[:, :, :F].index_select(0, plan.gather_index).permute(1, 2, 0).reshape(B, F, s.Hc, s.Wc)
+        # virtual edge element: every (cell, slot) whose neighbour is outside the grid (models.py:316)
+        n_nb = len(s.offsets)
+        d_edge = (d_in[:, :, F:].reshape(HW, B, n_nb, E) * plan.missing_dev[:, None, :, None]).sum((0, 1, 2))
+
+        grads = []
+        for mlp, n_heads, head_sizes in ((box_mlp, 2, (8, P)), (enc_mlp, 1, None), (z_mlp, 2, (2, P)), (obj_mlp, 1, None)):
+            dWs, dbs = mlp.weight_grads()
+            for dW, db in zip(dWs[:-1], dbs[:-1]):
+                grads += [dW, db]
+            if n_heads == 1:
+                grads += [dWs[-1], dbs[-1]]
+            else:
+                a = head_sizes[0]
+                grads += [dWs[-1][:a], dbs[-1][:a], dWs[-1][a:], dbs[-1][a:]]
+        assert len(grads) == ctx.n_params
+        # plan, x, feat, edge, eps_where, eps_attr, eps_depth, u_pres, wheel, *params
+        return (None, None, d_feat, d_edge, None, None, None, None, None) + tuple(grads)

@@ -1,0 +1,129 @@
+"""Shared helpers for the parity tests."""
+import contextlib
+import copy
+import io
+import os
+import zlib
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL, ATOL = 1e-4, 1e-5       # BASELINE.json north_star: fp32 parity tolerance
+
+CONFIG_OVERRIDES = {
+    "A": {},
+    "tiny": dict(INPUT_IMAGE_SHAPE=[1, 40, 40], OBJECT_SHAPE=[8, 8], ANCHORBOX_SHAPE=[16, 16], topology="cell8"),
+    "C": dict(OBJECT_SHAPE=[14, 14], topology="cell8"),
+    "D": dict(INPUT_IMAGE_SHAPE=[3, 256, 256], topology="cell8"),
+    "rgb64": dict(INPUT_IMAGE_SHAPE=[3, 64, 64], OBJECT_SHAPE=[14, 14], topology="cell8"),
+}
+
+
+class NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+    add_image = add_figure = add_histogram = add_scalar
+
+
+@contextlib.contextmanager
+def spair_config(name):
+    """Temporarily set spair_pytorch_b200.config to one of the named shape configs."""
+    from spair_pytorch_b200 import config as cfg
+    ov = dict(CONFIG_OVERRIDES[name])
+    topo = ov.pop("topology", None)
+    saved = {k: copy.deepcopy(getattr(cfg, k)) for k in list(ov) + ["DEFAULT_BACKBONE_TOPOLOGY"]}
+    try:
+        for k, v in ov.items():
+            setattr(cfg, k, copy.deepcopy(v))
+        if topo == "cell8":
+            cfg.DEFAULT_BACKBONE_TOPOLOGY = copy.deepcopy(cfg.CELL8_BACKBONE_TOPOLOGY)
+        yield cfg
+    finally:
+        for k, v in saved.items():
+            setattr(cfg, k, v)
+
+
+def build_model(name, device="cpu", seed=3):
+    """SPAIR built under torch.manual_seed(seed) (reference train.py:39-41) for a named config."""
+    from spair_pytorch_b200.models import SPAIR
+    with spair_config(name) as cfg:
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = SPAIR(list(cfg.INPUT_IMAGE_SHAPE), NullWriter(), torch.device(device))
+    return net.to(device)
+
+
+def oracle_config(name):
+    from oracle import spair_oracle as so
+    return dict(A=so.config_A, tiny=so.config_tiny, C=so.config_C, D=so.config_D,
+                rgb64=lambda: so.OracleConfig(image_shape=(3, 64, 64), object_shape=(14, 14),
+                                              topology=copy.deepcopy(so.CELL8_TOPOLOGY)))[name]()
+
+
+def load_golden(fname):
+    return np.load(os.path.join(GOLDEN_DIR, fname))
+
+
+def grad_sample_indices(name, numel, n_sample=1024, full_max=2048):
+    if numel <= max(full_max, n_sample):
+        return np.arange(numel)
+    rs = np.random.RandomState(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    return np.sort(rs.choice(numel, n_sample, replace=False))
+
+
+def assert_close(actual, expected, what, rtol=RTOL, atol=ATOL):
+    a = torch.as_tensor(actual).detach().cpu().double()
+    e = torch.as_tensor(expected).detach().cpu().double()
+    assert a.shape == e.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(e.shape))
+    err = (a - e).abs()
+    tol = atol + rtol * e.abs()
+    if not bool((err <= tol).all()):
+        i = int(torch.argmax(err - tol))
+        raise AssertionError("%s: %d/%d outside rtol=%g atol=%g; worst |diff|=%.3e at flat %d (got %.9g, want %.9g)"
+                             % (what, int((err > tol).sum()), err.numel(), rtol, atol, err.flatten()[i].item(), i,
+                                a.flatten()[i].item(), e.flatten()[i].item()))
+
+
+def check_model_against_golden(net, g, device):
+    """Runs one forward+backward of ``net`` on the golden's inputs and compares everything the
+    golden holds: parameters (checksums), loss, canvas, latents, KL maps, parameter gradients."""
+    for k, v in net.state_dict().items():
+        d = v.detach().cpu().double()
+        s = np.array([d.sum().item(), d.abs().sum().item()])
+        assert np.array_equal(s, g["psum/" + k]), "parameter %s differs from the reference's seeded init" % k
+    x = torch.from_numpy(g["x"]).to(device)
+    net.set_noise(*(torch.from_numpy(g[k]) for k in ("eps_where", "eps_attr", "eps_depth", "u_pres")))
+    for p in net.parameters():
+        p.grad = None
+    loss, recon, z_where, z_pres = net(x, int(g["step"]))
+    loss.backward(retain_graph=True)
+    assert_close(loss, g["loss"], "loss")
+    assert_close(recon, g["recon_x"], "recon_x")
+    assert_close(z_where, g["z_where"], "z_where")
+    assert_close(z_pres, g["z_pres"], "z_pres")
+    lat = net.latent_maps()
+    assert_close(lat["z_attr"], g["z_attr"], "z_attr")
+    assert_close(lat["z_depth"], g["z_depth"], "z_depth")
+    for n, m in net.kl_maps().items():
+        assert_close(m, g["kl/" + n], "KL map " + n)
+    for n, p in net.dist_param.items():
+        assert_close(p["mean"], g["dist_mean/" + n], "dist mean " + n)
+        assert_close(p["sigma"], g["dist_std/" + n], "dist sigma " + n)
+    worst = {}
+    for k, p in net.named_parameters():
+        if "gnone/" + k in g.files:
+            assert p.grad is None, "%s must not receive a gradient (reference: grad is None)" % k
+            continue
+        assert p.grad is not None, "%s has no gradient" % k
+        gr = p.grad.detach().cpu().flatten()
+        idx = torch.from_numpy(g["gidx/" + k])
+        want = torch.from_numpy(g["gval/" + k])
+        # gradient tolerance is relative to the scale of the tensor (individual entries cancel to ~0)
+        scale = float(g["gstat/" + k][1]) / max(np.sqrt(gr.numel()), 1.0)
+        assert_close(gr[idx], want, "grad " + k, rtol=RTOL, atol=ATOL + RTOL * scale)
+        stat = np.array([gr.double().sum().item(), gr.double().norm().item()])
+        assert abs(stat[1] - g["gstat/" + k][1]) <= 1e-4 * g["gstat/" + k][1] + 1e-7, "grad norm of %s" % k
+        worst[k] = float((gr[idx] - want).abs().max())
+    return worst
