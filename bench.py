@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — SPAIR per-cell object pipeline, train images/sec (fwd+bwd) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1]): spair/config.py defaults (1x128x128 canvas, 11x11 cells,
+28x28 glimpses, 50 attributes), batch 256 PER GPU (weak scaling), procedurally generated
+scattered-sprite scenes, fp32 everywhere, global_step >= 1000 so that every gradient is live.
+A "step" is what reference train.py:64-67 does: zero grads, forward, backward, Adam step (plus the
+NCCL gradient allreduce when N > 1).
+
+One JSON line is printed by rank 0:
+  value        whole-job images/s with the input batch already resident in HBM
+  e2e          same metric through the public API with HOST inputs: every step copies the batch from
+               pinned host memory to the device and reads the loss back to the host
+  roofline     the dominant hand-written kernel (fused render backward), timed in isolation with CUDA
+               events and an L2 flush between launches, against MEASURED_PEAKS.json's HBM copy peak
+  cpu_baseline the CPU oracle (a restatement of the reference's op sequence, oracle/spair_oracle.py)
+               timed on this box's host cores on a bounded sample (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train images/sec (fwd+bwd)"
+UNIT = "images/s"
+PER_GPU_BATCH = 256
+CONFIG_NAME = "A"          # spair/config.py defaults
+STEP0 = 1000               # training wheel off: all gradients live
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+    add_image = add_figure = add_histogram = add_scalar
+
+
+def make_batches(n_batches, batch, image_shape, seed):
+    from spair_pytorch_b200.dataloader import scattered_sprites
+    return [scattered_sprites(batch, image_shape, seed=seed + 1000 * i).pin_memory() for i in range(n_batches)]
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def kernel_roofline(net, x, steps=20):
+    """Times the hand-written warp kernels in isolation on the tensors of a real step (CUDA events on
+    the launching stream, L2 flushed between launches) and converts to GB/s with the ALGORITHMIC bytes
+    of SURVEY.md §8(d) / DESIGN.md."""
+    from spair_pytorch_b200 import kernels as K
+    dev = x.device
+    B, C, I, _ = x.shape
+    L = net._latents
+    HW = L.Hc * L.Wc
+    G = net._cfg.object_shape[0]
+    N = B * HW
+    with torch.no_grad():
+        logits = net.object_decoder(L.attr.reshape(N, -1)).contiguous()
+    zw, zd, zp = L.z_where.reshape(N, 4).contiguous(), L.depth.reshape(-1).contiguous(), L.pres.reshape(-1).contiguous()
+    recon = torch.empty(B, C, I, I, device=dev)
+    denom = torch.empty(B, I, I, device=dev)
+    partial = torch.empty(K.render_num_tiles(B, I, I), device=dev)
+    gs = torch.empty(B, C + 1, I, I, device=dev)
+    d_logits, d_zw, d_zd, d_zp = torch.empty_like(logits), torch.empty_like(zw), torch.empty_like(zd), torch.empty_like(zp)
+    cells = torch.arange(HW, dtype=torch.int32, device=dev)
+    glimpses = torch.empty(N, C * G * G, device=dev)
+    d_gl = torch.randn(N, C * G * G, device=dev)
+    d_zw_l = torch.empty(N, 4, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    scales = net._cfg.scales
+
+    def t_render_fwd():
+        K.render_fwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, x, partial)
+
+    def t_render_bwd():
+        K.render_bwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, None, x, None, gs, d_logits, d_zw, d_zd, d_zp)
+
+    def t_glimpse_fwd():
+        K.glimpse_fwd(x, L.z_where, cells, B, HW, G, G, glimpses)
+
+    def t_glimpse_bwd():
+        K.glimpse_bwd(x, L.z_where, cells, B, HW, G, G, d_gl, d_zw_l, None)
+
+    # algorithmic bytes per image
+    per_image = {
+        "render_fwd": HW * (4 * (C + 1) * G * G + 24) + 4 * C * I * I,
+        "render_bwd": 4 * C * I * I + HW * (8 * (C + 1) * G * G + 48),
+        "glimpse_fwd": 4 * C * I * I + HW * (16 + 4 * C * G * G),
+        "glimpse_bwd": 4 * C * I * I + HW * (4 * C * G * G + 32),
+    }
+    peak, peak_src = measured_hbm_peak()
+    out = {}
+    for name, fn in (("render_fwd", t_render_fwd), ("render_bwd", t_render_bwd), ("glimpse_fwd", t_glimpse_fwd),
+                     ("glimpse_bwd", t_glimpse_bwd)):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(steps):
+            flush.fill_(1.0)                      # 256 MB > 126 MB L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.mean(times)
+        nbytes = per_image[name] * B
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "bytes": nbytes, "achieved": gbs, "frac": gbs / peak}
+    dom = max(out, key=lambda k: out[k]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": out[dom]["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": out[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": out[dom]["bytes"], "ms_per_launch": out[dom]["ms"],
+            "timing": "CUDA events on the launching stream, 256 MB L2 flush between launches, mean of %d" % steps}
+    return roof, out
+
+
+def cpu_baseline(sample_batch=32, iters=2):
+    """The CPU oracle (port of the reference's op sequence) on this host: forward + backward."""
+    from oracle import spair_oracle as so
+    from tests import helpers
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = helpers.oracle_config(CONFIG_NAME)
+    net = helpers.build_model(CONFIG_NAME)
+    params = so.params_from_state_dict(net.state_dict())
+    x = so.scattered_sprites(sample_batch, cfg.image_shape, seed=1234)
+    noise = so.random_noise(torch.Generator().manual_seed(7), sample_batch, cfg.grid, cfg.n_attr)
+    so.forward_backward(params, x[:2], STEP0 + 1, so.Noise(*(t[:2] for t in (noise.eps_where, noise.eps_attr, noise.eps_depth,
+                                                                               noise.u_pres))), cfg)   # warm-up
+    t0 = time.time()
+    for _ in range(iters):
+        so.forward_backward(params, x, STEP0 + 1, noise, cfg)
+    dt = (time.time() - t0) / iters
+    return {"value": sample_batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d timed fwd+bwd iterations of batch %d (config defaults, step %d) after 1 warm-up; %.2f s/iter"
+                      % (iters, sample_batch, STEP0 + 1, dt)}
+
+
+def run_ours(args):
+    from spair_pytorch_b200 import dp, kernels as K
+    from tests import helpers
+    rank, world, local_rank = dp.init_distributed("nccl" if "RANK" in os.environ else None)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    net = helpers.build_model(CONFIG_NAME, dev)
+    ddp = dp.DataParallelSPAIR(net, world_size=world)
+    ddp.broadcast_parameters()
+    opt = torch.optim.Adam([p for _, p in dp.trainable_parameters(net)], lr=1e-4)
+    B = args.batch
+    image_shape = tuple(net.image_shape)
+    host_batches = make_batches(4, B, image_shape, seed=1234 + rank)
+    dev_batches = [b.to(dev) for b in host_batches]
+    x_stage = torch.empty_like(dev_batches[0])
+    loss_host = torch.empty((), pin_memory=True)
+    torch.manual_seed(7 + rank)
+
+    def step_resident(i):
+        ddp.step(dev_batches[i % len(dev_batches)], STEP0 + i)
+        opt.step()
+
+    def step_e2e(i):
+        x_stage.copy_(host_batches[i % len(host_batches)], non_blocking=True)      # H2D from pinned memory
+        loss = ddp.step(x_stage, STEP0 + i)[0]
+        opt.step()
+        loss_host.copy_(loss.detach(), non_blocking=False)                          # D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        n0 = K.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms) / steps, K.launch_count() - n0, clk.summary()
+
+    ms_res, launches, clocks = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    value = world * B / (ms_res * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        roof, per_kernel = kernel_roofline(net, dev_batches[0])
+        HW = net._latents.Hc * net._latents.Wc
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: spair/config.py defaults (1x128x128 canvas, 11x11 cells, 28x28 glimpses), "
+                                   "batch %d per GPU, procedural scattered sprites, step = zero_grad+fwd+bwd+Adam%s"
+                                   % (B, "+NCCL grad allreduce" if world > 1 else ""),
+                       "per_gpu_batch": B, "global_batch": world * B, "objects_per_image": HW, "global_step": STEP0,
+                       "parallelism": "dp%d" % world, "tf32": False,
+                       "l2": "per-step working set (~2.3 KB x %d objects x fwd+bwd buffers, > 1 GB) exceeds the 126 MB L2; "
+                             "kernel timings flush L2 between launches" % (B * HW)},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": world * host_batches[0].numel() * 4,
+                    "d2h_bytes_per_step": world * 4},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "kernels": per_kernel,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return line
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own algorithm on the host CPU (oracle port; the Python reference
+# itself cannot travel to the GPU box)
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import spair_oracle as so
+    from tests import helpers
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = helpers.oracle_config(CONFIG_NAME)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = helpers.build_model(CONFIG_NAME)
+    params = so.params_from_state_dict(net.state_dict())
+    # bounded sample: calibrate on 2 images, then pick a batch so that steps+warmup stay within ~150 s
+    probe = 2
+    xs = so.scattered_sprites(32, cfg.image_shape, seed=1234)
+    noise = so.random_noise(torch.Generator().manual_seed(7), 32, cfg.grid, cfg.n_attr)
+
+    def sub(n):
+        return xs[:n], so.Noise(noise.eps_where[:n], noise.eps_attr[:n], noise.eps_depth[:n], noise.u_pres[:n])
+
+    t0 = time.time()
+    so.forward_backward(params, *[sub(probe)[0]], STEP0 + 1, sub(probe)[1], cfg)
+    t_probe = time.time() - t0
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    batch = int(max(1, min(32, probe * budget / max(t_probe, 1e-3))))
+    x, nz = sub(batch)
+    for _ in range(args.warmup):
+        so.forward_backward(params, x, STEP0 + 1, nz, cfg)
+    t0 = time.time()
+    for i in range(args.steps):
+        so.forward_backward(params, x, STEP0 + 1 + i, nz, cfg)
+    dt = (time.time() - t0) / max(args.steps, 1)
+    value = batch / dt
+    sample = ("oracle port of the reference's CPU op sequence (per-cell loop, materialised render), batch %d per step, "
+              "%d ATen threads; the Python reference itself cannot travel to the GPU box" % (batch, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] workload (spair/config.py defaults), bounded sample of batch %d per step "
+                                   "on the host CPU, step = fwd+bwd" % batch, "per_step_batch": batch, "global_step": STEP0 + 1},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun when asked for N > 1 from a plain `python bench.py`
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    with contextlib.redirect_stdout(sys.stderr):   # keep stdout for the JSON line only
+        pass
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,13 @@ extern "C" {
 
 int spair_abi_version(void);
 
+/* HOST helper (no device work): out[j] = the j-th normalised base coordinate of an n-point axis, i.e.
+ * torch's `linspace(-1, 1, n) * (n - 1) / n` as used by F.affine_grid(align_corners=False)
+ * (reference modules.py:265), reproduced bit-exactly in fp32.  The kernels evaluate the same
+ * expression on the device; this entry point exists so the coordinate parity can be checked
+ * without a GPU. */
+int spair_base_grid(int n, float* out /* host, n floats */);
+
 /* Box decode constants (host struct).  models.py:339-374, config.py:34,38-41. */
 typedef struct spair_box_geom {
     float yx_scale;     /* MAX_YX - MIN_YX */

@@ -289,6 +289,12 @@ static size_t glimpse_smem(int Gh, int Gw, bool bwd) {
     return sizeof(float) * (size_t)(kTileW * kTileH + (bwd ? 2 : 1) * (Gh + Gw));
 }
 
+extern "C" int spair_base_grid(int n, float* out) {
+    SPAIR_REQUIRE(n > 0 && out);
+    for (int j = 0; j < n; ++j) out[j] = base_coord(j, n);
+    return 0;
+}
+
 extern "C" int spair_glimpse_fwd(const float* image, const float* z_where, const int* cells, int n_cells, int B,
                                  int HW, int C, int Ih, int Iw, int Gh, int Gw, float* out, int ld_out,
                                  void* stream) {

@@ -34,6 +34,7 @@ class SpairKernelError(RuntimeError):
 _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 _SIGNATURES = {
     "spair_abi_version": [],
+    "spair_base_grid": [_I, _P],
     "spair_context_gather_fwd": [_P] * 6 + [_P, _I, _P, _I] + [_I] * 5 + [_P, _I, _P, _I, _P, _I, _P],
     "spair_context_grad_gather": [_P, _I, _P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "spair_box_head_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _I, _P],
@@ -89,7 +90,26 @@ def require_cuda(t, what="input"):
                                "has no CPU implementation" % what)
 
 
+def base_grid(n: int) -> torch.Tensor:
+    """Host helper: the n-point normalised base grid the kernels use (see spair_base_grid)."""
+    out = torch.empty(n, dtype=torch.float32)
+    _check(lib().spair_base_grid(n, out.data_ptr()), "spair_base_grid")
+    return out
+
+
+# kernels launched per C-ABI call (render_bwd = prep + object kernel; paste_bwd's memset is not a kernel)
+_LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0}
+LAUNCH_COUNT = 0
+
+
+def launch_count() -> int:
+    """Number of libspair_b200 kernel launches issued by this process so far."""
+    return LAUNCH_COUNT
+
+
 def _check(code: int, name: str) -> None:
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL.get(name, 1)
     if code != 0:
         if code < 0:
             raise SpairKernelError("%s rejected its arguments (SPAIR_ERR_INVALID)" % name)

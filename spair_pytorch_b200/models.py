@@ -58,10 +58,15 @@ class SPAIR(nn.Module):
         self.pixels_per_cell = tuple(int(i) for i in self.backbone.grid_cell_size)
         self._plan = None
         self._noise = None
+        self.kl_scale = 1.0          # 1/world_size under data parallelism (dp.py), 1 otherwise
         self.dist_param, self.dist = {}, {}
         if "SPAIR_ALLOW_TF32" not in os.environ:   # fp32 parity with the reference's CPU path
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
+        if "SPAIR_NONDETERMINISTIC_CUDNN" not in os.environ:
+            # the hand-written kernels are bitwise reproducible; keep the cuDNN convs that way too
+            # (its default backward-filter algorithm for the 1-channel first conv uses atomics)
+            torch.backends.cudnn.deterministic = True
         print('model initialized')
 
     # ------------------------------------------------------------------------------------
@@ -191,7 +196,7 @@ class SPAIR(nn.Module):
                                                           pres.reshape(-1), x, B, HW, C, plan.G, Ih, Iw, c.scales)
         kl_sums, kl_map = ops.KLFunction.apply(dmean, dstd, pres, plan.prior_mean, plan.prior_std, count_dist0, c.n_attr)
         kl_means = kl_sums.mean(dim=0)                       # batch mean of per-image sums (models.py:553)
-        loss = recon_loss + c.beta * kl_means.sum()          # models.py:558
+        loss = recon_loss + (c.beta * self.kl_scale) * kl_means.sum()   # models.py:558
 
         # side attributes the reference keeps (models.py:44-48,122-125) — views, no extra compute
         self._latents = SimpleNamespace(z_where=z_where, box=box, attr=attr, depth=depth, pres=pres, dmean=dmean,

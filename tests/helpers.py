@@ -111,7 +111,7 @@ def check_model_against_golden(net, g, device):
     for n, p in net.dist_param.items():
         assert_close(p["mean"], g["dist_mean/" + n], "dist mean " + n)
         assert_close(p["sigma"], g["dist_std/" + n], "dist sigma " + n)
-    worst = {}
+    worst, failures = {}, []
     for k, p in net.named_parameters():
         if "gnone/" + k in g.files:
             assert p.grad is None, "%s must not receive a gradient (reference: grad is None)" % k
@@ -122,8 +122,12 @@ def check_model_against_golden(net, g, device):
         want = torch.from_numpy(g["gval/" + k])
         # gradient tolerance is relative to the scale of the tensor (individual entries cancel to ~0)
         scale = float(g["gstat/" + k][1]) / max(np.sqrt(gr.numel()), 1.0)
-        assert_close(gr[idx], want, "grad " + k, rtol=RTOL, atol=ATOL + RTOL * scale)
-        stat = np.array([gr.double().sum().item(), gr.double().norm().item()])
-        assert abs(stat[1] - g["gstat/" + k][1]) <= 1e-4 * g["gstat/" + k][1] + 1e-7, "grad norm of %s" % k
+        try:
+            assert_close(gr[idx], want, "grad " + k, rtol=RTOL, atol=ATOL + RTOL * scale)
+            stat = np.array([gr.double().sum().item(), gr.double().norm().item()])
+            assert abs(stat[1] - g["gstat/" + k][1]) <= 1e-4 * g["gstat/" + k][1] + 1e-7, "grad norm of %s" % k
+        except AssertionError as e:
+            failures.append(str(e))
         worst[k] = float((gr[idx] - want).abs().max())
+    assert not failures, "\n".join(failures)
     return worst

@@ -1,0 +1,123 @@
+"""Model-level parity on the B200: SPAIR.forward + loss.backward through the C-ABI kernels against
+(a) golden vectors produced by the unmodified reference and (b) the CPU oracle run on the same
+seeded inputs; plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("name,step", [("tiny", 1), ("tiny", 1001), ("A", 1), ("A", 1001)])
+def test_model_matches_reference_golden(name, step):
+    net = helpers.build_model(name, DEV)
+    g = helpers.load_golden("model_%s_step%d.npz" % (name, step))
+    helpers.check_model_against_golden(net, g, DEV)
+
+
+def _run_oracle(net, x, step, noise, name):
+    from oracle import spair_oracle as so
+    cfg = helpers.oracle_config(name)
+    params = so.params_from_state_dict(net.state_dict())
+    out = so.forward_backward(params, x, step, noise, cfg, check_finite=False)
+    return out, params
+
+
+@pytest.mark.parametrize("name,B,step", [("C", 2, 1001), ("rgb64", 2, 1001), ("A", 3, 2500)])
+def test_model_vs_oracle_other_shapes(name, B, step):
+    """16x16 cells / 14x14 glimpses (config C), RGB with 8x8 cells, and a later training step, checked
+    against the oracle executed on the host in the same test."""
+    from oracle import spair_oracle as so
+    net = helpers.build_model(name, DEV)
+    cfg = helpers.oracle_config(name)
+    x = so.scattered_sprites(B, cfg.image_shape, seed=11, sprite_px=(8, 20))
+    noise = so.random_noise(torch.Generator().manual_seed(5), B, cfg.grid, cfg.n_attr)
+    want, params = _run_oracle(net, x, step, noise, name)
+    net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)
+    loss, recon, z_where, z_pres = net(x.to(DEV), step)
+    loss.backward(retain_graph=True)
+    assert_close(loss, want["loss"], "loss")
+    assert_close(recon, want["recon_x"], "recon_x")
+    assert_close(z_where, want["z_where"], "z_where")
+    assert_close(z_pres, want["z_pres"], "z_pres")
+    assert_close(net.latent_maps()["z_attr"], want["z_attr"], "z_attr")
+    for n, m in net.kl_maps().items():
+        assert_close(m, want["kl"][n], "KL " + n)
+    failures = []
+    for k, p in net.named_parameters():
+        if k.startswith("attn."):
+            assert p.grad is None
+            continue
+        ref = params[k].grad
+        scale = float(ref.norm()) / np.sqrt(ref.numel())
+        try:
+            assert_close(p.grad, ref, "grad " + k, atol=1e-5 + 1e-4 * scale)
+        except AssertionError as e:
+            failures.append(str(e))
+    assert not failures, "\n".join(failures)
+
+
+def test_full_size_config_B_properties():
+    """BASELINE config 2 (defaults, batch 256) at full size: finite loss/gradients, bitwise
+    run-to-run determinism, and the data-parallel identity — two half batches with the KL term
+    scaled by 1/2 give the gradients of the whole batch."""
+    from oracle import spair_oracle as so
+    net = helpers.build_model("A", DEV)
+    B = 256
+    x = so.scattered_sprites(B, (1, 128, 128), seed=2).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    noise = so.random_noise(g, B, (11, 11), 50)
+
+    def run(sl, kl_scale):
+        net.kl_scale = kl_scale
+        net.set_noise(noise.eps_where[sl], noise.eps_attr[sl], noise.eps_depth[sl], noise.u_pres[sl])
+        for p in net.parameters():
+            p.grad = None
+        loss = net(x[sl], 1500)[0]
+        loss.backward()
+        return loss.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    full = slice(0, B)
+    loss1, g1 = run(full, 1.0)
+    loss2, g2 = run(full, 1.0)
+    assert torch.isfinite(loss1) and torch.equal(loss1, loss2)
+    nondet = [k for k in g1 if not torch.equal(g1[k], g2[k])]
+    assert not nondet, "non-deterministic gradients: %s" % nondet
+    for k in g1:
+        assert torch.isfinite(g1[k]).all(), k
+    la, ga = run(slice(0, B // 2), 0.5)
+    lb, gb = run(slice(B // 2, B), 0.5)
+    net.kl_scale = 1.0
+    assert_close(la + lb, loss1, "sum of shard losses")
+    failures = []
+    for k in g1:
+        scale = float(g1[k].norm()) / np.sqrt(g1[k].numel())
+        try:
+            assert_close(ga[k] + gb[k], g1[k], "sharded grad " + k, atol=1e-5 + 2e-4 * scale)
+        except AssertionError as e:
+            failures.append(str(e))
+    assert not failures, "\n".join(failures)
+
+
+def test_reference_training_loop_runs():
+    """The reference's train.py step (zero_grad / forward / backward(retain_graph=True) / Adam step,
+    train.py:64-67) on procedural scenes: loss stays finite and decreases over a few steps."""
+    from oracle import spair_oracle as so
+    net = helpers.build_model("A", DEV)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    x = so.scattered_sprites(32, (1, 128, 128), seed=4).to(DEV)
+    losses = []
+    noise = so.random_noise(torch.Generator().manual_seed(0), 32, (11, 11), 50)
+    for it in range(8):
+        opt.zero_grad()
+        net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)   # fixed draws: deterministic objective
+        loss, out_img, z_where, z_pres = net(x, 1000 + it)
+        loss.backward(retain_graph=True)
+        opt.step()
+        losses.append(float(loss))
+        assert out_img.shape == x.shape and z_where.shape == (32, 4, 11, 11) and z_pres.shape == (32, 1, 11, 11)
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
