@@ -136,7 +136,7 @@ def backbone_geometry(topology, image_hw):
 
 def exponential_decay(global_step, start, end, decay_rate, decay_step, staircase=False, log_space=False):
     """modules.py:191-213, evaluated in fp32 tensors exactly as there."""
-    gs = torch.tensor(global_step, dtype=torch.float32)
+    gs = torch.tensor(global_step, dtype=torch.get_default_dtype())
     t = gs // decay_step if staircase else gs / decay_step
     value = (start - end) * (decay_rate ** t) + end
     if log_space:
@@ -301,7 +301,7 @@ def build_obj_pres(logit, u, wheel):
 
 def count_prior_distribution(step, n_cells, cfg: OracleConfig):
     """models.py:184-193: truncated geometric prior over the object count."""
-    support = torch.arange(n_cells + 1, dtype=torch.float32)
+    support = torch.arange(n_cells + 1, dtype=torch.get_default_dtype())
     log_odds = exponential_decay(step, **cfg.count_prior)
     prob = 1 / ((-log_odds).exp() + 1)
     dist = (1 - prob) * (prob ** support)
@@ -450,13 +450,13 @@ def forward(params, x, global_step, noise: Noise, cfg: OracleConfig, check_finit
                 z_depth=z_depth, z_pres=z_pres, kl=kl, dist_mean=dist_mean, dist_std=dist_std, feat=feat)
 
 
-def params_from_state_dict(state_dict, requires_grad=True):
-    """Detached fp32 CPU copies of a SPAIR ``state_dict`` (reference key names),
-    as leaves that can receive gradients.  ``attn.*`` entries are carried but never used
-    (models.py:120 discards the attention output)."""
+def params_from_state_dict(state_dict, requires_grad=True, dtype=torch.float32):
+    """Detached CPU copies (fp32 by default) of a SPAIR ``state_dict`` (reference key names,
+    SURVEY.md §8(b)), as leaves that can receive gradients.  ``attn.*`` entries are carried but never
+    used (models.py:120 discards the attention output)."""
     out = {}
     for k, v in state_dict.items():
-        t = v.detach().to("cpu", torch.float32).clone()
+        t = v.detach().to("cpu", dtype).clone()
         t.requires_grad_(requires_grad and not k.startswith("attn."))
         out[k] = t
     return out
@@ -469,6 +469,27 @@ def forward_backward(params, x, global_step, noise, cfg, check_finite=True):
     out = forward(params, x, global_step, noise, cfg, check_finite)
     out["loss"].backward()
     return out
+
+
+def forward_backward_fp64(state_dict, x, global_step, noise, cfg):
+    """The same op sequence evaluated in float64 — the "true" value of the reference's formulas.
+
+    Needed because the reference's own fp32 backward is ill-conditioned on some inputs: the
+    importance normalisation (models.py:527-535) makes d(loss)/d(importance) a difference of nearly
+    equal numbers at singly-covered pixels, and BCE gradients reach 1e12 on uncovered pixels
+    (SURVEY.md §7).  On such inputs the reference's fp32 gradients differ from this fp64 evaluation by
+    up to tens of percent, so no independent implementation can match them to 1e-4; the parity tests then
+    require the CUDA result to be at least as close to fp64 as the fp32 reference path is.
+    Returns (out dict, params dict with .grad in float64)."""
+    saved = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        params = params_from_state_dict(state_dict, dtype=torch.float64)
+        n64 = Noise(*(t.double() for t in (noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)))
+        out = forward_backward(params, x.double(), global_step, n64, cfg, check_finite=False)
+    finally:
+        torch.set_default_dtype(saved)
+    return out, params
 
 
 # --------------------------------------------------------------------------------------

@@ -517,7 +517,11 @@ static int launch_fwd(const RenderArgs& a, cudaStream_t st) {
     p.slot_f4 = slot_f4;
     const size_t smem = group * slot_bytes + (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
-    cudaFuncSetAttribute(render_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_set = 0;   // benign cache: the attribute only ever grows
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(render_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
     dim3 grid((p.Iw + kRTileW - 1) / kRTileW, (p.Ih + kRTileH - 1) / kRTileH, p.B);
     render_fwd_kernel<C><<<grid, kRThreads, smem, st>>>(p);
     SPAIR_LAUNCH_CHECK();
@@ -535,7 +539,11 @@ static int launch_bwd(const RenderBwdArgs& p, const float* recon, const float* d
     const size_t smem = (size_t)p.G * p.G * Tex<C>::NF4 * sizeof(float4) +
                         sizeof(float) * ((size_t)kBandPix * (C + 2) + kBandMaxW + kBandPix);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
-    cudaFuncSetAttribute(render_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(render_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
     render_bwd_kernel<C><<<(unsigned)((size_t)p.B * p.HW), kRThreads, smem, st>>>(p);
     SPAIR_LAUNCH_CHECK();
 }

@@ -1,0 +1,55 @@
+"""CUDA-graph capture of the training step (forward + backward of the whole hot path).
+
+One SPAIR step at the default config is ~2,000 kernel launches (31 wavefronts x (cuBLAS GEMMs + head /
+glimpse kernels), forward and backward) of a few microseconds each, so an eagerly launched step is bound by
+the host's launch rate, not by the GPU.  ``GraphedTrainStep`` captures zero-grad + forward + backward once
+(after warm-up on a side stream) and replays it: per step the host only refreshes the two step-dependent
+schedules (``SPAIR.prepare_step``), copies the batch into the static input and launches one graph.  The
+gradient allreduce (dp.py) and the optimiser step stay outside the graph.
+
+Requirements: gradients live in a ``dp.GradientBucket`` (static memory, zeroed inside the graph); the batch
+shape is fixed; noise is drawn on the device inside the graph (PyTorch's graph-safe Philox generator
+advances per replay); the writer is not called from a captured step.
+"""
+from __future__ import annotations
+
+import torch
+
+from .dp import GradientBucket, trainable_parameters
+
+
+class GraphedTrainStep:
+    def __init__(self, net, example_x: torch.Tensor, bucket: GradientBucket = None, global_step: int = 1000, warmup: int = 3):
+        if not example_x.is_cuda:
+            raise ValueError("GraphedTrainStep needs a CUDA batch")
+        self.net = net
+        self.bucket = bucket if bucket is not None else GradientBucket(trainable_parameters(net))
+        self.static_x = example_x.detach().clone().float().contiguous()
+        dev = example_x.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # builds the plan, cuBLAS/cuDNN handles, func attributes
+                self.bucket.zero()
+                net(self.static_x, global_step)[0].backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        net.prepare_step(global_step, dev)
+        self.graph = torch.cuda.CUDAGraph()
+        net._static_step = True
+        try:
+            with torch.cuda.graph(self.graph):
+                self.bucket.zero()
+                self.out = net(self.static_x, global_step)
+                self.out[0].backward()
+        finally:
+            net._static_step = False
+        self.bucket.check_attached()
+
+    def __call__(self, x: torch.Tensor, global_step: int):
+        """Runs one captured step on ``x`` (device tensor, or pinned host tensor — copied asynchronously).
+        Returns the static output tuple (loss, recon_x, z_where, z_pres); gradients are in the bucket."""
+        self.net.prepare_step(global_step, self.static_x.device)
+        self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -59,6 +59,8 @@ class SPAIR(nn.Module):
         self._plan = None
         self._noise = None
         self.kl_scale = 1.0          # 1/world_size under data parallelism (dp.py), 1 otherwise
+        self._step_state = None      # per-device step scalars (training wheel, count prior)
+        self._static_step = False    # True while a captured CUDA graph owns the step (graphed.py)
         self.dist_param, self.dist = {}, {}
         if "SPAIR_ALLOW_TF32" not in os.environ:   # fp32 parity with the reference's CPU path
             torch.backends.cudnn.allow_tf32 = False
@@ -156,6 +158,32 @@ class SPAIR(nn.Module):
 
         return multi(self.box_network) + seq(self.object_encoder) + multi(self.z_network) + seq(self.obj_network)
 
+    def prepare_step(self, global_step, device):
+        """Host side of one step: evaluates the two schedules that depend on ``global_step`` — the
+        training wheel (models.py:59) and the count prior (models.py:184-193) — in fp32 exactly as the
+        reference does, and ships them to two small persistent device buffers (1 and HW+1 floats) through
+        a ring of pinned staging buffers, so no step ever synchronises with the host.  Called by
+        ``forward`` itself, or by ``GraphedTrainStep`` before replaying a captured step."""
+        _, Hc, Wc = (int(v) for v in self.feature_space_dim)
+        HW = Hc * Wc
+        st = self._step_state
+        if st is None or st.wheel.device != device:
+            ring = 64
+            st = SimpleNamespace(wheel=torch.zeros(1, device=device), count=torch.zeros(HW + 1, device=device),
+                                 pin=torch.zeros(ring, HW + 2).pin_memory() if device.type == "cuda" else torch.zeros(ring, HW + 2),
+                                 slot=0, ring=ring)
+            self._step_state = st
+        self.global_step = global_step
+        wheel_host = exponential_decay(global_step, 'cpu', **self._cfg.wheel)
+        self.training_wheel = wheel_host
+        row = st.pin[st.slot]
+        st.slot = (st.slot + 1) % st.ring
+        row[0] = wheel_host
+        row[1:] = self._count_prior(HW)
+        st.wheel.copy_(row[:1], non_blocking=True)
+        st.count.copy_(row[1:], non_blocking=True)
+        return st
+
     def _count_prior(self, HW):
         """Truncated geometric prior over the object count, evaluated in fp32 on the host exactly as
         the reference does (models.py:184-193), then shipped to the device ([HW+1] floats)."""
@@ -176,15 +204,16 @@ class SPAIR(nn.Module):
         HW = Hc * Wc
         B = x.shape[0]
         C, Ih, Iw = plan.C, plan.Ih, plan.Iw
-        self.global_step, self.batch_size = global_step, B
+        self.batch_size = B
+        if self._static_step:
+            st = self._step_state            # filled by prepare_step() before the graph is replayed
+        else:
+            st = self.prepare_step(global_step, dev)
+            self.writer.add_scalar('training_wheel', self.training_wheel, global_step)
+        wheel, count_dist0 = st.wheel, st.count
 
         x = x.float().contiguous()
         feat = self.backbone(x)
-        wheel_host = exponential_decay(global_step, 'cpu', **c.wheel)
-        self.training_wheel = wheel_host
-        self.writer.add_scalar('training_wheel', wheel_host, global_step)
-        wheel = wheel_host.reshape(1).to(dev, non_blocking=True)
-        count_dist0 = self._count_prior(HW).to(dev, non_blocking=True)
         noise = self._draw_noise(B, HW, dev)
 
         z_where, attr, depth, pres, dmean, dstd, box = ops.CellSweepFunction.apply(
@@ -202,7 +231,8 @@ class SPAIR(nn.Module):
         self._latents = SimpleNamespace(z_where=z_where, box=box, attr=attr, depth=depth, pres=pres, dmean=dmean,
                                         dstd=dstd, kl_map=kl_map, kl_sums=kl_sums, recon_loss=recon_loss, Hc=Hc, Wc=Wc)
         self._publish_dist_params(B, Hc, Wc)
-        self._log_losses(loss, recon_loss, kl_means)
+        if not self._static_step:
+            self._log_losses(loss, recon_loss, kl_means)
 
         z_where_out = z_where.permute(0, 2, 1).reshape(B, 4, Hc, Wc)
         z_pres_out = pres.reshape(B, 1, Hc, Wc)

@@ -37,6 +37,7 @@ def test_model_vs_oracle_other_shapes(name, B, step):
     x = so.scattered_sprites(B, cfg.image_shape, seed=11, sprite_px=(8, 20))
     noise = so.random_noise(torch.Generator().manual_seed(5), B, cfg.grid, cfg.n_attr)
     want, params = _run_oracle(net, x, step, noise, name)
+    _, params64 = so.forward_backward_fp64(net.state_dict(), x, step, noise, cfg)
     net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)
     loss, recon, z_where, z_pres = net(x.to(DEV), step)
     loss.backward(retain_graph=True)
@@ -55,7 +56,9 @@ def test_model_vs_oracle_other_shapes(name, B, step):
         ref = params[k].grad
         scale = float(ref.norm()) / np.sqrt(ref.numel())
         try:
-            assert_close(p.grad, ref, "grad " + k, atol=1e-5 + 1e-4 * scale)
+            how = helpers.assert_close_or_as_accurate(p.grad, ref, params64[k].grad, "grad " + k, atol=1e-5 + 1e-4 * scale)
+            if how != "fp32":
+                print("grad %s judged against %s" % (k, how))
         except AssertionError as e:
             failures.append(str(e))
     assert not failures, "\n".join(failures)
@@ -121,3 +124,33 @@ def test_reference_training_loop_runs():
         losses.append(float(loss))
         assert out_img.shape == x.shape and z_where.shape == (32, 4, 11, 11) and z_pres.shape == (32, 1, 11, 11)
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_graphed_step_equals_eager_step():
+    """The CUDA-graph replay of zero-grad + forward + backward gives bitwise the gradients of the eager
+    step on the same batch and noise, and can be replayed on new batches / steps."""
+    from oracle import spair_oracle as so
+    from spair_pytorch_b200 import dp
+    from spair_pytorch_b200.graphed import GraphedTrainStep
+    net = helpers.build_model("tiny", DEV)
+    B = 8
+    xs = [so.scattered_sprites(B, (1, 40, 40), seed=s, sprite_px=(6, 14)).to(DEV) for s in (1, 2)]
+    noise = so.random_noise(torch.Generator().manual_seed(3), B, (5, 5), 50)
+    dev_noise = [t.to(DEV) for t in (noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)]
+    bucket = dp.GradientBucket(dp.trainable_parameters(net))
+
+    def eager(x, step):
+        bucket.zero()
+        net.set_noise(*dev_noise)
+        loss = net(x, step)[0]
+        loss.backward()
+        return loss.detach().clone(), bucket.flat.clone()
+
+    want = [eager(xs[0], 1200), eager(xs[1], 3000)]
+    net.set_noise(*dev_noise)                       # device-resident noise becomes a static input of the graph
+    gstep = GraphedTrainStep(net, xs[0], bucket=bucket, global_step=1200)
+    for (x, step), (loss_w, grad_w) in zip(((xs[0], 1200), (xs[1], 3000)), want):
+        loss = gstep(x, step)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(loss, loss_w)
+        assert torch.equal(bucket.flat, grad_w)
