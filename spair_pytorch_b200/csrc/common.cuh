@@ -54,6 +54,10 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
     }
 }
 
+// exact floor(i / d) for 0 <= i < 2^15, 1 <= d <= 2^10 without an integer division (inv_d = 1.0f / d):
+// (i + 0.5) / d is at least 0.5/d away from an integer, far more than the fp32 rounding of the product
+__device__ __forceinline__ int fast_div(int i, float inv_d) { return (int)(((float)i + 0.5f) * inv_d); }
+
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 
 struct NeighbourList {

@@ -108,6 +108,8 @@ glimpse_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
     const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
     const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, nullptr, nullptr, aligned != 0);
     const int GG = Gh * Gw;
+    const bool small = GG < (1 << 15) && Gw <= 1024;
+    const float inv_Gw = 1.0f / (float)Gw;
     for (int c = 0; c < C; ++c) {
         const float* plane = image + ((long long)b * C + c) * Ih * Iw;
         if (w.staged) {
@@ -116,7 +118,7 @@ glimpse_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
         }
         float* orow = out + (long long)r * ld_out + (long long)c * GG;
         for (int t = threadIdx.x; t < GG; t += blockDim.x) {
-            const int i = t / Gw, j = t - i * Gw;
+            const int i = small ? fast_div(t, inv_Gw) : t / Gw, j = t - i * Gw;
             const float ix = col_ix[j], iy = row_iy[i];
             const float fx0 = floorf(ix), fy0 = floorf(iy);
             const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
@@ -141,7 +143,11 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
     float* row_iy = col_ix + Gw;
     float* col_m = row_iy + Gh;
     float* row_m = col_m + Gw;
+    float* col_b = row_m + Gh;      // normalised base coordinates (d gx / d xs, d gy / d ys)
+    float* row_b = col_b + Gw;
     __shared__ float red[4 * (kGlimpseThreads / 32)];
+    for (int j = threadIdx.x; j < Gw; j += blockDim.x) col_b[j] = base_coord(j, Gw);
+    for (int i = threadIdx.x; i < Gh; i += blockDim.x) row_b[i] = base_coord(i, Gh);
     const int r = blockIdx.x;
     const int b = cells ? r % B : r;
     const long long o = cells ? (long long)b * HW + cells[r / B] : r;
@@ -149,6 +155,8 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
     const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
     const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, col_m, row_m, aligned != 0);
     const int GG = Gh * Gw;
+    const bool small = GG < (1 << 15) && Gw <= 1024;
+    const float inv_Gw = 1.0f / (float)Gw;
     // acc[0] = sum dL/dgx, acc[1] = sum dL/dgy, acc[2] = sum dL/dgx * base_x, acc[3] = sum dL/dgy * base_y
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int c = 0; c < C; ++c) {
@@ -160,7 +168,7 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
         }
         const float* grow = d_out + (long long)r * ld_out + (long long)c * GG;
         for (int t = threadIdx.x; t < GG; t += blockDim.x) {
-            const int i = t / Gw, j = t - i * Gw;
+            const int i = small ? fast_div(t, inv_Gw) : t / Gw, j = t - i * Gw;
             const float ix = col_ix[j], iy = row_iy[i];
             const float fx0 = floorf(ix), fy0 = floorf(iy);
             const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
@@ -173,8 +181,8 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
             const float dgx = gix * col_m[j], dgy = giy * row_m[i];
             acc[0] += dgx;
             acc[1] += dgy;
-            acc[2] += dgx * base_coord(j, Gw);
-            acc[3] += dgy * base_coord(i, Gh);
+            acc[2] = fmaf(dgx, col_b[j], acc[2]);
+            acc[3] = fmaf(dgy, row_b[i], acc[3]);
             if (gplane) {
                 const bool x1ok = x0 + 1 <= Iw - 1, y1ok = y0 + 1 <= Ih - 1;
                 float* p = gplane + (long long)y0 * Iw + x0;
@@ -286,7 +294,7 @@ __global__ void paste_bwd_kernel(const float* __restrict__ image, const float* _
 using namespace spair;
 
 static size_t glimpse_smem(int Gh, int Gw, bool bwd) {
-    return sizeof(float) * (size_t)(kTileW * kTileH + (bwd ? 2 : 1) * (Gh + Gw));
+    return sizeof(float) * (size_t)(kTileW * kTileH + (bwd ? 3 : 1) * (Gh + Gw));
 }
 
 extern "C" int spair_base_grid(int n, float* out) {

@@ -27,10 +27,13 @@
 
 namespace spair {
 
-constexpr int kRTileW = 32, kRTileH = 16, kRThreads = 256;
+constexpr int kRTileW = 32, kRThreads = 256;
+constexpr int kRPPT = 4;                      // canvas rows per thread in the forward kernel
+constexpr int kRTileH = (kRThreads / kRTileW) * kRPPT;   // 32
 constexpr int kRMaxGroup = 8;
 constexpr int kBandPix = 1024;   // pixels per backward band
 constexpr int kBandMaxW = 64;    // footprint columns per chunk
+constexpr int kBandMaxH = 256;   // footprint rows per band
 
 struct RenderArgs {
     const float* logits;
@@ -53,7 +56,10 @@ struct Tex {
     float v[NF4 * 4];
 };
 
-__device__ __forceinline__ float sigmoid_analytical(float x) { return 1.0f / (expf(-x) + 1.0f); }  // modules.py:187
+// 1/(exp(-x)+1) (modules.py:187) with the SFU exponential and reciprocal: |error| <= 2e-7 for |x| <= 10
+// (exp relative error <= 2^-22 + 6e-8|x|), far inside the 1e-5 parity tolerance; saturates to exactly 0 / 1
+// like the reference for |x| > ~17 / 88.
+__device__ __forceinline__ float sigmoid_analytical(float x) { return __fdividef(1.0f, __expf(-x) + 1.0f); }
 
 // decode one texel: colours, alpha (with presence), importance  (models.py:485-500)
 template <int C>
@@ -93,7 +99,8 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     constexpr int NF4 = Tex<C>::NF4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* slots = reinterpret_cast<float4*>(smem_raw);
-    unsigned short* list = reinterpret_cast<unsigned short*>(slots + (size_t)p.group * p.slot_f4);
+    float4* aff = slots + (size_t)p.group * p.slot_f4;                          // [HW] inverse affine of kept objects
+    unsigned short* list = reinterpret_cast<unsigned short*>(aff + p.HW);       // [HW] kept object ids, cell order
     __shared__ int warp_cnt[kRThreads / 32];
     __shared__ int list_len;
     __shared__ float red[kRThreads / 32];
@@ -110,8 +117,9 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     for (int k0 = 0; k0 < p.HW; k0 += kRThreads) {
         const int k = k0 + threadIdx.x;
         bool hit = false;
+        float4 zw = make_float4(0.f, 0.f, 1.f, 1.f);
         if (k < p.HW) {
-            const float4 zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + (size_t)b * p.HW + k);
+            zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + (size_t)b * p.HW + k);
             int xl, xh, yl, yh;
             footprint(zw.x, zw.z, p.Iw, G, xl, xh);
             footprint(zw.y, zw.w, p.Ih, G, yl, yh);
@@ -122,7 +130,12 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
         __syncthreads();
         int off = list_len;
         for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-        if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        if (hit) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            const InvAffine A(zw.x, zw.y, zw.z, zw.w);
+            list[pos] = (unsigned short)k;
+            aff[pos] = make_float4(A.ax, A.cx, A.ay, A.cy);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
@@ -133,34 +146,44 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     }
     const int n_list = list_len;
 
-    // ---- per-thread pixels: column tx, rows ty and ty + 8 ----
+    // ---- per-thread pixels: column tx, rows ty + 8*h ----
     const int tx = threadIdx.x & (kRTileW - 1), ty = threadIdx.x / kRTileW;
     const int X = X0 + tx;
-    const int Ya = Y0 + ty, Yb = Y0 + ty + kRTileH / 2;
-    const bool pa = X < p.Iw && Ya < p.Ih, pb = X < p.Iw && Yb < p.Ih;
+    const bool px_ok = X < p.Iw;
     const float bX = base_coord(min(X, p.Iw - 1), p.Iw);
-    const float bYa = base_coord(min(Ya, p.Ih - 1), p.Ih), bYb = base_coord(min(Yb, p.Ih - 1), p.Ih);
+    float bY[kRPPT];
+    bool ok[kRPPT];
+#pragma unroll
+    for (int h = 0; h < kRPPT; ++h) {
+        const int Y = Y0 + ty + (kRThreads / kRTileW) * h;
+        ok[h] = px_ok && Y < p.Ih;
+        bY[h] = base_coord(min(Y, p.Ih - 1), p.Ih);
+    }
     const float bX0 = base_coord(X0, p.Iw), bX1 = base_coord(X1, p.Iw);
     const float bY0 = base_coord(Y0, p.Ih), bY1 = base_coord(Y1, p.Ih);
     const float hG = 0.5f * (float)G;
 
-    float num[2][C];
-    float den[2] = {0.0f, 0.0f};
-    int ncov[2] = {0, 0};
+    float num[kRPPT][C];
+    float den[kRPPT];
+    int ncov[kRPPT];
 #pragma unroll
-    for (int c = 0; c < C; ++c) num[0][c] = num[1][c] = 0.0f;
+    for (int h = 0; h < kRPPT; ++h) {
+        den[h] = 0.0f;
+        ncov[h] = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) num[h][c] = 0.0f;
+    }
 
     // ---- 2./3. stage K objects, composite, repeat ----
     for (int g0 = 0; g0 < n_list; g0 += p.group) {
         const int gcount = min(p.group, n_list - g0);
         for (int s = 0; s < gcount; ++s) {
             const int k = list[g0 + s];
+            const float4 A = aff[g0 + s];
             const size_t n = (size_t)b * p.HW + k;
-            const float4 zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + n);
-            const InvAffine A(zw.x, zw.y, zw.z, zw.w);
             // texel sub-rectangle reachable from this tile (coordinates are monotone in X / Y)
-            const float ixa = unnormalize(affine_coord(bX0, A.ax, A.cx), hG), ixb = unnormalize(affine_coord(bX1, A.ax, A.cx), hG);
-            const float iya = unnormalize(affine_coord(bY0, A.ay, A.cy), hG), iyb = unnormalize(affine_coord(bY1, A.ay, A.cy), hG);
+            const float ixa = unnormalize(affine_coord(bX0, A.x, A.y), hG), ixb = unnormalize(affine_coord(bX1, A.x, A.y), hG);
+            const float iya = unnormalize(affine_coord(bY0, A.z, A.w), hG), iyb = unnormalize(affine_coord(bY1, A.z, A.w), hG);
             const int tx_lo = max(0, (int)floorf(fmaxf(fminf(ixa, ixb), -1.0f)));
             const int tx_hi = min(G - 1, (int)floorf(fminf(fmaxf(ixa, ixb), (float)G)) + 1);
             const int ty_lo = max(0, (int)floorf(fmaxf(fminf(iya, iyb), -1.0f)));
@@ -170,8 +193,9 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
             const float depth = __ldg(p.z_depth + n), pres = __ldg(p.z_pres + n);
             float4* slot = slots + (size_t)s * p.slot_f4;
             const float* base = p.logits + n * (size_t)(G * G * (C + 1));
+            const float inv_tw = 1.0f / (float)tw;
             for (int t = threadIdx.x; t < tw * th; t += kRThreads) {
-                const int ry = t / tw, rx = t - ry * tw;
+                const int ry = fast_div(t, inv_tw), rx = t - ry * tw;
                 const int tex = (ty_lo + ry) * G + tx_lo + rx;
                 float l[C + 1];
                 load_logits<C>(base + (size_t)tex * (C + 1), l);
@@ -186,21 +210,18 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
         }
         __syncthreads();
         for (int s = 0; s < gcount; ++s) {
-            const int k = list[g0 + s];
-            const size_t n = (size_t)b * p.HW + k;
-            const float4 zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + n);
-            const InvAffine A(zw.x, zw.y, zw.z, zw.w);
+            const float4 A = aff[g0 + s];
             const float4* slot = slots + (size_t)s * p.slot_f4;
-            const float ix = unnormalize(affine_coord(bX, A.ax, A.cx), hG);
+            const float ix = unnormalize(affine_coord(bX, A.x, A.y), hG);
             const float fx0 = floorf(ix);
             if (!(fx0 >= -1.0f && fx0 <= (float)(G - 1))) continue;
             const int x0 = (int)fx0;
             const float wx1 = (x0 + 1 <= G - 1) ? ix - fx0 : 0.0f, wx0 = (x0 >= 0) ? fx0 + 1.0f - ix : 0.0f;
             const int xa = max(x0, 0), xb = min(x0 + 1, G - 1);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (!(h == 0 ? pa : pb)) continue;
-                const float iy = unnormalize(affine_coord(h == 0 ? bYa : bYb, A.ay, A.cy), hG);
+            for (int h = 0; h < kRPPT; ++h) {
+                if (!ok[h]) continue;
+                const float iy = unnormalize(affine_coord(bY[h], A.z, A.w), hG);
                 const float fy0 = floorf(iy);
                 if (!(fy0 >= -1.0f && fy0 <= (float)(G - 1))) continue;
                 const int y0 = (int)fy0;
@@ -231,9 +252,9 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     // ---- epilogue: normalise, clamp, store, fused BCE ----
     float bce = 0.0f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        if (!(h == 0 ? pa : pb)) continue;
-        const int Y = h == 0 ? Ya : Yb;
+    for (int h = 0; h < kRPPT; ++h) {
+        if (!ok[h]) continue;
+        const int Y = Y0 + ty + (kRThreads / kRTileW) * h;
         const float S = den[h] + (float)(p.HW - ncov[h]) * 1e-9f;          // every object adds 1e-9 (models.py:527,532)
         const size_t pix = (size_t)Y * p.Iw + X;
         if (p.denom) p.denom[(size_t)b * p.Ih * p.Iw + pix] = S;
@@ -303,17 +324,28 @@ struct RenderBwdArgs {
     float* d_z_pres;
 };
 
+constexpr int kOutside = -1000000;   // marks a footprint column / row whose sample falls outside the texture
+
 template <int C>
-__global__ void __launch_bounds__(kRThreads) render_bwd_kernel(RenderBwdArgs p) {
+__global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs p) {
     constexpr int NF4 = Tex<C>::NF4;
     constexpr int NCH = C + 2;
     constexpr int QMAX = 4;   // texels owned per thread (G*G <= 1024)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int G = p.G, GG = G * G;
-    float4* tex = reinterpret_cast<float4*>(smem_raw);                 // [GG][NF4]
-    float* pixg = reinterpret_cast<float*>(tex + (size_t)GG * NF4);    // [kBandPix][NCH]
-    float* col_ix = pixg + kBandPix * NCH;                             // [kBandMaxW]
-    float* row_iy = col_ix + kBandMaxW;                                // [kBandPix]  (band rows <= kBandPix)
+    const int G = p.G, GG = G * G, GP = G + 2;
+    // decoded texels with a one-texel zero border: zeros padding needs no tap masks
+    float4* tex = reinterpret_cast<float4*>(smem_raw);                 // [GP*GP][NF4]
+    float* pixg = reinterpret_cast<float*>(tex + (size_t)GP * GP * NF4);   // [kBandPix][NCH] per-pixel gradients
+    float* col_fx = pixg + kBandPix * NCH;                             // [kBandMaxW] fractional sample position
+    float* col_bx = col_fx + kBandMaxW;                                // [kBandMaxW] normalised canvas coordinate
+    int* col_x0 = reinterpret_cast<int*>(col_bx + kBandMaxW);          // [kBandMaxW] floor(sample position)
+    float* row_fy = reinterpret_cast<float*>(col_x0 + kBandMaxW);      // [kBandMaxH]
+    float* row_by = row_fy + kBandMaxH;
+    int* row_y0 = reinterpret_cast<int*>(row_by + kBandMaxH);
+    int* tcol_lo = row_y0 + kBandMaxH;                                 // [32] first/last footprint column feeding texel column j
+    int* tcol_hi = tcol_lo + 32;
+    int* trow_lo = tcol_hi + 32;
+    int* trow_hi = trow_lo + 32;
     __shared__ float red[6 * (kRThreads / 32)];
 
     const size_t n = blockIdx.x;
@@ -322,16 +354,20 @@ __global__ void __launch_bounds__(kRThreads) render_bwd_kernel(RenderBwdArgs p) 
     const float depth = __ldg(p.z_depth + n), pres = __ldg(p.z_pres + n);
     const InvAffine A(zw.x, zw.y, zw.z, zw.w);
     const float hG = 0.5f * (float)G;
+    const float inv_G = 1.0f / (float)G, inv_GP = 1.0f / (float)GP;
     const float* lbase = p.logits + n * (size_t)(GG * (C + 1));
 
-    // ---- 0. stage decoded texels ----
-    for (int t = threadIdx.x; t < GG; t += kRThreads) {
-        float l[C + 1];
-        load_logits<C>(lbase + (size_t)t * (C + 1), l);
+    // ---- 0. stage decoded texels (zero border) ----
+    for (int t = threadIdx.x; t < GP * GP; t += kRThreads) {
+        const int yp = fast_div(t, inv_GP), xp = t - yp * GP;
         Tex<C> o;
 #pragma unroll
         for (int i = 0; i < NF4 * 4; ++i) o.v[i] = 0.0f;
-        decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, o.v);
+        if (yp >= 1 && yp <= G && xp >= 1 && xp <= G) {
+            float l[C + 1];
+            load_logits<C>(lbase + (size_t)((yp - 1) * G + xp - 1) * (C + 1), l);
+            decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, o.v);
+        }
 #pragma unroll
         for (int q = 0; q < NF4; ++q) tex[(size_t)t * NF4 + q] = make_float4(o.v[4 * q], o.v[4 * q + 1], o.v[4 * q + 2], o.v[4 * q + 3]);
     }
@@ -349,57 +385,87 @@ __global__ void __launch_bounds__(kRThreads) render_bwd_kernel(RenderBwdArgs p) 
     float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // sum dgx, sum dgy, sum dgx*bX, sum dgy*bY, d_depth, d_pres
     const size_t npix = (size_t)p.Ih * p.Iw;
     const float* gs_b = p.gs + (size_t)b * (C + 1) * npix;
-    // approximate inverse maps texel -> pixel, used only to bound the gather loops (exact weights decide)
-    const float sx = (float)G / (zw.z * (float)p.Iw), sy = (float)G / (zw.w * (float)p.Ih);
-    const float ox = hG - 0.5f - sx * (zw.x * (float)p.Iw - 0.5f), oy = hG - 0.5f - sy * (zw.y * (float)p.Ih - 0.5f);
+    // texel coordinates of this thread's texels
+    int t_i[QMAX], t_j[QMAX];
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) {
+        const int t = threadIdx.x + q * kRThreads;
+        t_i[q] = fast_div(t, inv_G);
+        t_j[q] = t - t_i[q] * G;
+    }
     __syncthreads();
 
     for (int Xc = Xlo; Xc <= Xhi; Xc += kBandMaxW) {
         const int cw = min(kBandMaxW, Xhi - Xc + 1);
-        const int rows_per_band = kBandPix / cw;
-        for (int j = threadIdx.x; j < cw; j += kRThreads)
-            col_ix[j] = unnormalize(affine_coord(base_coord(Xc + j, p.Iw), A.ax, A.cx), hG);
+        const float inv_cw = 1.0f / (float)cw;
+        // balanced bands of at most min(kBandPix / cw, kBandMaxH) rows
+        const int n_rows = Yhi - Ylo + 1;
+        const int max_rows = min(kBandPix / cw, kBandMaxH);
+        const int n_bands = (n_rows + max_rows - 1) / max_rows;
+        const int rows_per_band = n_bands > 0 ? (n_rows + n_bands - 1) / n_bands : 1;
+        // ---- column tables of this chunk ----
+        if (threadIdx.x < 32) { tcol_lo[threadIdx.x] = 1 << 30; tcol_hi[threadIdx.x] = -1; }
+        __syncthreads();
+        for (int j = threadIdx.x; j < cw; j += kRThreads) {
+            const float bX = base_coord(Xc + j, p.Iw);
+            const float ix = unnormalize(affine_coord(bX, A.ax, A.cx), hG);
+            const float f0 = floorf(ix);
+            const bool in = f0 >= -1.0f && f0 <= (float)(G - 1);
+            const int x0 = in ? (int)f0 : kOutside;
+            col_x0[j] = x0;
+            col_fx[j] = ix - f0;
+            col_bx[j] = bX;
+            if (in) {
+                if (x0 >= 0) { atomicMin(&tcol_lo[x0], j); atomicMax(&tcol_hi[x0], j); }
+                if (x0 + 1 <= G - 1) { atomicMin(&tcol_lo[x0 + 1], j); atomicMax(&tcol_hi[x0 + 1], j); }
+            }
+        }
         for (int Yb = Ylo; Yb <= Yhi; Yb += rows_per_band) {
             const int rh = min(rows_per_band, Yhi - Yb + 1);
-            for (int i = threadIdx.x; i < rh; i += kRThreads)
-                row_iy[i] = unnormalize(affine_coord(base_coord(Yb + i, p.Ih), A.ay, A.cy), hG);
+            if (threadIdx.x < 32) { trow_lo[threadIdx.x] = 1 << 30; trow_hi[threadIdx.x] = -1; }
+            __syncthreads();
+            for (int i = threadIdx.x; i < rh; i += kRThreads) {
+                const float bY = base_coord(Yb + i, p.Ih);
+                const float iy = unnormalize(affine_coord(bY, A.ay, A.cy), hG);
+                const float f0 = floorf(iy);
+                const bool in = f0 >= -1.0f && f0 <= (float)(G - 1);
+                const int y0 = in ? (int)f0 : kOutside;
+                row_y0[i] = y0;
+                row_fy[i] = iy - f0;
+                row_by[i] = bY;
+                if (in) {
+                    if (y0 >= 0) { atomicMin(&trow_lo[y0], i); atomicMax(&trow_hi[y0], i); }
+                    if (y0 + 1 <= G - 1) { atomicMin(&trow_lo[y0 + 1], i); atomicMax(&trow_hi[y0 + 1], i); }
+                }
+            }
             __syncthreads();
             // ---- 1. per-pixel gradients ----
             for (int pp = threadIdx.x; pp < cw * rh; pp += kRThreads) {
-                const int py = pp / cw, px = pp - py * cw;
-                const float ix = col_ix[px], iy = row_iy[py];
-                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const int py = fast_div(pp, inv_cw), px = pp - py * cw;
+                const int x0 = col_x0[px], y0 = row_y0[py];
                 float out[NCH];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) out[c] = 0.0f;
-                if (fx0 >= -1.0f && fx0 <= (float)(G - 1) && fy0 >= -1.0f && fy0 <= (float)(G - 1)) {
-                    const int x0 = (int)fx0, y0 = (int)fy0;
-                    const bool vxa = x0 >= 0, vxb = x0 + 1 <= G - 1, vya = y0 >= 0, vyb = y0 + 1 <= G - 1;
-                    const float wx1 = vxb ? ix - fx0 : 0.0f, wx0 = vxa ? fx0 + 1.0f - ix : 0.0f;
-                    const float wy1 = vyb ? iy - fy0 : 0.0f, wy0 = vya ? fy0 + 1.0f - iy : 0.0f;
-                    // derivative weights: an out-of-range tap has value 0 but still bounds the cell
-                    const float ex0 = vxa ? 1.0f : 0.0f, ex1 = vxb ? 1.0f : 0.0f, ey0 = vya ? 1.0f : 0.0f, ey1 = vyb ? 1.0f : 0.0f;
-                    const float uy1 = iy - fy0, uy0 = fy0 + 1.0f - iy, ux1 = ix - fx0, ux0 = fx0 + 1.0f - ix;
-                    const int xa = max(x0, 0), xb = min(x0 + 1, G - 1), ya = max(y0, 0), yb = min(y0 + 1, G - 1);
+                if (x0 != kOutside && y0 != kOutside) {
+                    const float wx1 = col_fx[px], wy1 = row_fy[py];
+                    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;       // == (x0+1) - ix, exactly
                     const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0), sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
+                    const float4* tp = tex + (size_t)((y0 + 1) * GP + x0 + 1) * NF4;   // padded coordinates
                     float v[NF4 * 4], dvx[NF4 * 4], dvy[NF4 * 4];
 #pragma unroll
                     for (int q = 0; q < NF4; ++q) {
-                        const float4 t00 = tex[(size_t)(ya * G + xa) * NF4 + q], t01 = tex[(size_t)(ya * G + xb) * NF4 + q];
-                        const float4 t10 = tex[(size_t)(yb * G + xa) * NF4 + q], t11 = tex[(size_t)(yb * G + xb) * NF4 + q];
+                        const float4 t00 = tp[q], t01 = tp[NF4 + q], t10 = tp[(size_t)GP * NF4 + q], t11 = tp[(size_t)(GP + 1) * NF4 + q];
                         const float a00[4] = {t00.x, t00.y, t00.z, t00.w}, a01[4] = {t01.x, t01.y, t01.z, t01.w};
                         const float a10[4] = {t10.x, t10.y, t10.z, t10.w}, a11[4] = {t11.x, t11.y, t11.z, t11.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             v[4 * q + e] = fmaf(a11[e], se, fmaf(a10[e], sw, fmaf(a01[e], ne, __fmul_rn(a00[e], nw))));
-                            // grid_sampler_2d_backward with zero padding: taps outside contribute value 0
-                            const float p00 = a00[e] * ex0 * ey0, p01 = a01[e] * ex1 * ey0, p10 = a10[e] * ex0 * ey1, p11 = a11[e] * ex1 * ey1;
-                            dvx[4 * q + e] = (p01 - p00) * uy0 + (p11 - p10) * uy1;
-                            dvy[4 * q + e] = (p10 - p00) * ux0 + (p11 - p01) * ux1;
+                            // grid_sampler_2d_backward, zeros padding (border texels are 0)
+                            dvx[4 * q + e] = (a01[e] - a00[e]) * wy0 + (a11[e] - a10[e]) * wy1;
+                            dvy[4 * q + e] = (a10[e] - a00[e]) * wx0 + (a11[e] - a01[e]) * wx1;
                         }
                     }
-                    const int X = Xc + px, Y = Yb + py;
-                    const size_t pix = (size_t)Y * p.Iw + X;
+                    const size_t pix = (size_t)(Yb + py) * p.Iw + (Xc + px);
                     const float a = v[C], m = v[C + 1] + 1e-9f;
                     float T = 0.0f;
 #pragma unroll
@@ -419,38 +485,28 @@ __global__ void __launch_bounds__(kRThreads) render_bwd_kernel(RenderBwdArgs p) 
                     const float dgx = gix * hG, dgy = giy * hG;
                     acc[0] += dgx;
                     acc[1] += dgy;
-                    acc[2] += dgx * base_coord(X, p.Iw);
-                    acc[3] += dgy * base_coord(Y, p.Ih);
+                    acc[2] = fmaf(dgx, col_bx[px], acc[2]);
+                    acc[3] = fmaf(dgy, row_by[py], acc[3]);
                 }
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) pixg[(size_t)pp * NCH + c] = out[c];
             }
             __syncthreads();
-            // ---- 2. texels gather through the transposed bilinear weights ----
+            // ---- 2. texels gather through the transposed bilinear weights (exact ranges) ----
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {
-                const int t = threadIdx.x + q * kRThreads;
-                if (t >= GG) break;
-                const int ti = t / G, tj = t - ti * G;
-                // pixel ranges whose sample coordinate can fall in (tj-1, tj+1) / (ti-1, ti+1)
-                float xa_f = ((float)(tj - 1) - ox) / sx, xb_f = ((float)(tj + 1) - ox) / sx;
-                float ya_f = ((float)(ti - 1) - oy) / sy, yb_f = ((float)(ti + 1) - oy) / sy;
-                if (xa_f > xb_f) { const float s = xa_f; xa_f = xb_f; xb_f = s; }
-                if (ya_f > yb_f) { const float s = ya_f; ya_f = yb_f; yb_f = s; }
-                const int pxa = max((int)floorf(xa_f) - 1 - Xc, 0), pxb = min((int)ceilf(xb_f) + 1 - Xc, cw - 1);
-                const int pya = max((int)floorf(ya_f) - 1 - Yb, 0), pyb = min((int)ceilf(yb_f) + 1 - Yb, rh - 1);
+                if (threadIdx.x + q * kRThreads >= GG) break;
+                const int ti = t_i[q], tj = t_j[q];
+                const int pya = trow_lo[ti], pyb = trow_hi[ti], pxa = tcol_lo[tj], pxb = tcol_hi[tj];
                 for (int py = pya; py <= pyb; ++py) {
-                    const float iy = row_iy[py];
-                    const float wy = (iy >= (float)ti) ? (float)(ti + 1) - iy : iy - (float)(ti - 1);
-                    if (!(wy > 0.0f && wy <= 1.0f)) continue;
+                    const float fy = row_fy[py];
+                    const float wy = (row_y0[py] == ti) ? 1.0f - fy : fy;
+                    const float* grow = pixg + (size_t)py * cw * NCH;
                     for (int px = pxa; px <= pxb; ++px) {
-                        const float ix = col_ix[px];
-                        const float wx = (ix >= (float)tj) ? (float)(tj + 1) - ix : ix - (float)(tj - 1);
-                        if (!(wx > 0.0f && wx <= 1.0f)) continue;
-                        const float w = wx * wy;
-                        const float* g = pixg + (size_t)(py * cw + px) * NCH;
+                        const float fx = col_fx[px];
+                        const float w = wy * ((col_x0[px] == tj) ? 1.0f - fx : fx);
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) dT[q][c] = fmaf(w, g[c], dT[q][c]);
+                        for (int c = 0; c < NCH; ++c) dT[q][c] = fmaf(w, grow[px * NCH + c], dT[q][c]);
                     }
                 }
             }
@@ -469,12 +525,12 @@ __global__ void __launch_bounds__(kRThreads) render_bwd_kernel(RenderBwdArgs p) 
         float dl[C + 1];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float e = expf(-__fmul_rn(l[c], p.obj_scale));
-            const float s = 1.0f / (e + 1.0f);
+            const float e = __expf(-__fmul_rn(l[c], p.obj_scale));
+            const float s = __fdividef(1.0f, e + 1.0f);
             dl[c] = dT[q][c] * e * s * s * p.obj_scale;
         }
-        const float e = expf(-__fadd_rn(__fmul_rn(l[C], p.alpha_scale), p.alpha_bias));
-        const float s = 1.0f / (e + 1.0f);
+        const float e = __expf(-__fadd_rn(__fmul_rn(l[C], p.alpha_scale), p.alpha_bias));
+        const float s = __fdividef(1.0f, e + 1.0f);
         const float a = s * pres;
         float d_a = dT[q][C];
         if (__fmul_rn(a, depth) >= 0.01f) {                                  // clamp(min=0.01) passes the gradient (models.py:500)
@@ -510,12 +566,13 @@ static int launch_fwd(const RenderArgs& a, cudaStream_t st) {
     RenderArgs p = a;
     const int slot_f4 = p.G * p.G * Tex<C>::NF4;
     const size_t slot_bytes = (size_t)slot_f4 * sizeof(float4);
-    int group = (int)((96 * 1024) / slot_bytes);
+    int group = (int)((64 * 1024) / slot_bytes);
     if (group > kRMaxGroup) group = kRMaxGroup;
     if (group < 1) group = 1;
     p.group = group;
     p.slot_f4 = slot_f4;
-    const size_t smem = group * slot_bytes + (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
+    const size_t smem = group * slot_bytes + (size_t)p.HW * sizeof(float4) +
+                        (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
     static size_t smem_set = 0;   // benign cache: the attribute only ever grows
     if (smem > smem_set) {
@@ -536,8 +593,8 @@ static int launch_bwd(const RenderBwdArgs& p, const float* recon, const float* d
     render_bwd_prep_kernel<C><<<grid, 256, 0, st>>>(recon, denom, d_recon, target, bce_scale, p.B, p.Ih, p.Iw, gs_ws);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)p.G * p.G * Tex<C>::NF4 * sizeof(float4) +
-                        sizeof(float) * ((size_t)kBandPix * (C + 2) + kBandMaxW + kBandPix);
+    const size_t smem = (size_t)(p.G + 2) * (p.G + 2) * Tex<C>::NF4 * sizeof(float4) +
+                        sizeof(float) * ((size_t)kBandPix * (C + 2) + 3 * kBandMaxW + 3 * kBandMaxH + 4 * 32);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
     static size_t smem_set = 0;
     if (smem > smem_set) {

@@ -13,6 +13,8 @@ advances per replay); the writer is not called from a captured step.
 """
 from __future__ import annotations
 
+import gc
+
 import torch
 
 from .dp import GradientBucket, trainable_parameters
@@ -26,6 +28,10 @@ class GraphedTrainStep:
         self.bucket = bucket if bucket is not None else GradientBucket(trainable_parameters(net))
         self.static_x = example_x.detach().clone().float().contiguous()
         dev = example_x.device
+        # drop every reference to earlier autograd graphs: their AccumulateGrad nodes are bound to the stream they
+        # were created on and would drag the legacy stream into the capture
+        net._latents, net.dist_param, net.dist = None, {}, {}
+        gc.collect()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):

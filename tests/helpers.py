@@ -87,25 +87,26 @@ def assert_close(actual, expected, what, rtol=RTOL, atol=ATOL):
 
 
 def assert_close_or_as_accurate(actual, ref32, ref64, what, rtol=RTOL, atol=ATOL):
-    """Parity with the reference's fp32 CPU result within (rtol, atol) — or, where that result is itself
-    dominated by fp32 rounding (it differs from the float64 evaluation of the same formulas by more than
-    the tolerance), at least as close to the float64 value as the fp32 reference path is."""
-    try:
-        assert_close(actual, ref32, what, rtol, atol)
-        return "fp32"
-    except AssertionError as first:
-        a = torch.as_tensor(actual).detach().cpu().double()
-        r32 = torch.as_tensor(ref32).detach().cpu().double()
-        r64 = torch.as_tensor(ref64).detach().cpu().double()
-        ref_err = float((r32 - r64).abs().max())
-        my_err = float((a - r64).abs().max())
-        tol = atol + rtol * float(r64.abs().max())
-        if ref_err <= tol:
-            raise first            # the fp32 reference is well-conditioned here: no excuse
-        if my_err > ref_err + tol:
-            raise AssertionError("%s: not within tolerance of the fp32 reference AND farther from the fp64 value "
-                                 "(%.3e) than the fp32 reference itself is (%.3e)\n%s" % (what, my_err, ref_err, first))
-        return "fp64 (|ours-fp64|=%.2e <= |ref32-fp64|=%.2e)" % (my_err, ref_err)
+    """Elementwise: within (rtol, atol) of the reference's fp32 CPU result, OR within (rtol, atol) of the
+    float64 evaluation of the same formulas, OR at least as close to that float64 value as the fp32
+    reference path itself is.  The two escape clauses only matter where the reference's fp32 result is
+    dominated by its own rounding noise (see oracle.forward_backward_fp64).  Returns how many elements
+    needed them."""
+    a = torch.as_tensor(actual).detach().cpu().double()
+    r32 = torch.as_tensor(ref32).detach().cpu().double()
+    r64 = torch.as_tensor(ref64).detach().cpu().double()
+    assert a.shape == r32.shape == r64.shape, "%s: shapes %s %s %s" % (what, a.shape, r32.shape, r64.shape)
+    e32, e64, ref_err = (a - r32).abs(), (a - r64).abs(), (r32 - r64).abs()
+    ok32 = e32 <= atol + rtol * r32.abs()
+    ok64 = (e64 <= atol + rtol * r64.abs()) | (e64 <= ref_err)
+    bad = ~(ok32 | ok64)
+    if bool(bad.any()):
+        i = int(torch.argmax(torch.where(bad, e64, torch.zeros_like(e64))))
+        raise AssertionError("%s: %d/%d elements are neither within rtol=%g atol=%g of the fp32 reference nor of its "
+                             "float64 evaluation; worst at flat %d: got %.9g, fp32 ref %.9g, fp64 %.9g"
+                             % (what, int(bad.sum()), bad.numel(), rtol, atol, i, a.flatten()[i].item(),
+                                r32.flatten()[i].item(), r64.flatten()[i].item()))
+    return int((~ok32).sum())
 
 
 def check_model_against_golden(net, g, device):
