@@ -102,10 +102,11 @@ class SPAIR(nn.Module):
     # ------------------------------------------------------------------------------------
     # noise: the kernels take the random draws as inputs (SURVEY.md §8 RNG row)
     # ------------------------------------------------------------------------------------
-    def set_noise(self, eps_where=None, eps_attr=None, eps_depth=None, u_pres=None):
-        """Inject the draws of the NEXT forward, in the reference's layout: eps_where [B,4,Hc,Wc] in
-        (cy, cx, height, width) order, eps_attr [B,A,Hc,Wc], eps_depth and u_pres [B,1,Hc,Wc].
-        Without injection every forward draws fresh noise on the device."""
+    def set_noise(self, eps_where=None, eps_attr=None, eps_depth=None, u_pres=None, keep=False):
+        """Inject the draws of the NEXT forward (of every following forward if ``keep``), in the
+        reference's layout: eps_where [B,4,Hc,Wc] in (cy, cx, height, width) order, eps_attr [B,A,Hc,Wc],
+        eps_depth and u_pres [B,1,Hc,Wc].  Without injection every forward draws fresh noise on the device."""
+        self._keep_noise = keep
         if eps_where is None:
             self._noise = None
             return
@@ -119,7 +120,8 @@ class SPAIR(nn.Module):
     def _draw_noise(self, B, HW, device):
         A = self._cfg.n_attr
         if self._noise is not None:
-            noise, self._noise = tuple(t.to(device) for t in self._noise), None
+            noise = tuple(t.to(device) for t in self._noise)
+            self._noise = noise if getattr(self, "_keep_noise", False) else None
             return noise
         return (torch.randn(B, HW, 4, device=device), torch.randn(B, HW, A, device=device),
                 torch.randn(B, HW, device=device), torch.rand(B, HW, device=device))

@@ -149,7 +149,7 @@ def test_graphed_step_equals_eager_step():
         return loss.detach().clone(), bucket.flat.clone()
 
     want = [eager(xs[0], 1200), eager(xs[1], 3000)]
-    net.set_noise(*dev_noise)                       # device-resident noise becomes a static input of the graph
+    net.set_noise(*dev_noise, keep=True)            # device-resident noise becomes a static input of the graph
     gstep = GraphedTrainStep(net, xs[0], bucket=bucket, global_step=1200)
     for (x, step), (loss_w, grad_w) in zip(((xs[0], 1200), (xs[1], 3000)), want):
         loss = gstep(x, step)[0]
