@@ -209,8 +209,8 @@ class _ManualMLP:
     def forward(self, r0, r1):
         inp = self.X[r0:r1]
         for l, h in enumerate(self.H):
-            torch.addmm(self.b[l], inp, self.W[l].t(), out=h[r0:r1])
-            torch.relu_(h[r0:r1])
+            # bias + ReLU fused into the GEMM epilogue (cuBLASLt) instead of a separate elementwise launch
+            torch._addmm_activation(self.b[l], inp, self.W[l].t(), out=h[r0:r1])
             inp = h[r0:r1]
         torch.addmm(self.b[-1], inp, self.W[-1].t(), out=self.Y[r0:r1])
 
