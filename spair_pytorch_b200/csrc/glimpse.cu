@@ -60,12 +60,15 @@ __device__ __forceinline__ Window glimpse_setup(const FwdAffine& A, int Ih, int 
 
 __device__ __forceinline__ void stage_window(const float* __restrict__ plane, int Iw, const Window& w,
                                              float* __restrict__ tile) {
+    // 16 lanes per window row (a row holds at most kTileW / 4 = 18 128-bit vectors): no integer division
     const int vec_per_row = w.tw >> 2;
-    const int nvec = vec_per_row * w.th;
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-        const int ry = v / vec_per_row, rx = (v - ry * vec_per_row) << 2;
-        const float4 q = __ldg(reinterpret_cast<const float4*>(plane + (long long)(w.y_lo + ry) * Iw + w.x_lo + rx));
-        *reinterpret_cast<float4*>(tile + ry * w.tw + rx) = q;
+    const int sub = threadIdx.x & 15, rows_per_pass = blockDim.x >> 4;
+#pragma unroll 1
+    for (int ry = threadIdx.x >> 4; ry < w.th; ry += rows_per_pass) {
+        const float4* src = reinterpret_cast<const float4*>(plane + (long long)(w.y_lo + ry) * Iw + w.x_lo);
+        float4* dst = reinterpret_cast<float4*>(tile + ry * w.tw);
+#pragma unroll 1
+        for (int v = sub; v < vec_per_row; v += 16) dst[v] = __ldg(src + v);
     }
 }
 
@@ -96,20 +99,19 @@ __device__ __forceinline__ Taps fetch_taps(const float* __restrict__ plane, int 
 __global__ void __launch_bounds__(kGlimpseThreads)
 glimpse_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, const int* __restrict__ cells,
                    int B, int HW, int C, int Ih, int Iw, int Gh, int Gw, float* __restrict__ out, int ld_out,
-                   int aligned) {
+                   int aligned, float inv_Gw) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float* col_ix = tile + kTileW * kTileH;
     float* row_iy = col_ix + Gw;
-    const int r = blockIdx.x;
-    const int b = cells ? r % B : r;
-    const long long o = cells ? (long long)b * HW + cells[r / B] : r;
+    const int b = blockIdx.x;                                   // image
+    const int r = cells ? blockIdx.y * B + b : b;               // output row (k*B + b)
+    const long long o = cells ? (long long)b * HW + cells[blockIdx.y] : b;
     const float4 zw = *reinterpret_cast<const float4*>(z_where + o * 4);
     const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
     const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, nullptr, nullptr, aligned != 0);
     const int GG = Gh * Gw;
     const bool small = GG < (1 << 15) && Gw <= 1024;
-    const float inv_Gw = 1.0f / (float)Gw;
     for (int c = 0; c < C; ++c) {
         const float* plane = image + ((long long)b * C + c) * Ih * Iw;
         if (w.staged) {
@@ -136,7 +138,7 @@ glimpse_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
 __global__ void __launch_bounds__(kGlimpseThreads)
 glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, const int* __restrict__ cells,
                    int B, int HW, int C, int Ih, int Iw, int Gh, int Gw, const float* __restrict__ d_out, int ld_out,
-                   float* __restrict__ d_zw, float* __restrict__ d_image, int aligned) {
+                   float* __restrict__ d_zw, float* __restrict__ d_image, int aligned, float inv_Gw) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float* col_ix = tile + kTileW * kTileH;
@@ -148,15 +150,14 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
     __shared__ float red[4 * (kGlimpseThreads / 32)];
     for (int j = threadIdx.x; j < Gw; j += blockDim.x) col_b[j] = base_coord(j, Gw);
     for (int i = threadIdx.x; i < Gh; i += blockDim.x) row_b[i] = base_coord(i, Gh);
-    const int r = blockIdx.x;
-    const int b = cells ? r % B : r;
-    const long long o = cells ? (long long)b * HW + cells[r / B] : r;
+    const int b = blockIdx.x;                                   // image
+    const int r = cells ? blockIdx.y * B + b : b;               // output row (k*B + b)
+    const long long o = cells ? (long long)b * HW + cells[blockIdx.y] : b;
     const float4 zw = *reinterpret_cast<const float4*>(z_where + o * 4);
     const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
     const Window w = glimpse_setup(A, Ih, Iw, Gh, Gw, col_ix, row_iy, col_m, row_m, aligned != 0);
     const int GG = Gh * Gw;
     const bool small = GG < (1 << 15) && Gw <= 1024;
-    const float inv_Gw = 1.0f / (float)Gw;
     // acc[0] = sum dL/dgx, acc[1] = sum dL/dgy, acc[2] = sum dL/dgx * base_x, acc[3] = sum dL/dgy * base_y
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int c = 0; c < C; ++c) {
@@ -308,14 +309,16 @@ extern "C" int spair_glimpse_fwd(const float* image, const float* z_where, const
                                  void* stream) {
     SPAIR_REQUIRE(image && z_where && out && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
     SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
-    const int rows = cells ? n_cells * B : B;
+    SPAIR_REQUIRE(!cells || n_cells <= 65535);
+    const dim3 grid(B, cells ? n_cells : 1);
     const size_t smem = glimpse_smem(Gh, Gw, false);
     SPAIR_REQUIRE(smem <= 200 * 1024);
     const int aligned = (Iw % 4 == 0) && ((uintptr_t)image % 16 == 0);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(glimpse_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    glimpse_fwd_kernel<<<rows, kGlimpseThreads, smem, (cudaStream_t)stream>>>(image, z_where, cells, B, HW, C, Ih, Iw,
-                                                                              Gh, Gw, out, ld_out, aligned);
+    glimpse_fwd_kernel<<<grid, kGlimpseThreads, smem, (cudaStream_t)stream>>>(image, z_where, cells, B, HW, C, Ih, Iw,
+                                                                              Gh, Gw, out, ld_out, aligned,
+                                                                              1.0f / (float)Gw);
     SPAIR_LAUNCH_CHECK();
 }
 
@@ -324,14 +327,16 @@ extern "C" int spair_glimpse_bwd(const float* image, const float* z_where, const
                                  float* d_z_where_local, float* d_image, void* stream) {
     SPAIR_REQUIRE(image && z_where && d_out && d_z_where_local && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
     SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
-    const int rows = cells ? n_cells * B : B;
+    SPAIR_REQUIRE(!cells || n_cells <= 65535);
+    const dim3 grid(B, cells ? n_cells : 1);
     const size_t smem = glimpse_smem(Gh, Gw, true);
     SPAIR_REQUIRE(smem <= 200 * 1024);
     const int aligned = (Iw % 4 == 0) && ((uintptr_t)image % 16 == 0);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(glimpse_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    glimpse_bwd_kernel<<<rows, kGlimpseThreads, smem, (cudaStream_t)stream>>>(
-        image, z_where, cells, B, HW, C, Ih, Iw, Gh, Gw, d_out, ld_out, d_z_where_local, d_image, aligned);
+    glimpse_bwd_kernel<<<grid, kGlimpseThreads, smem, (cudaStream_t)stream>>>(
+        image, z_where, cells, B, HW, C, Ih, Iw, Gh, Gw, d_out, ld_out, d_z_where_local, d_image, aligned,
+        1.0f / (float)Gw);
     SPAIR_LAUNCH_CHECK();
 }
 

@@ -31,7 +31,7 @@ constexpr int kRTileW = 32, kRThreads = 256;
 constexpr int kRPPT = 4;                      // canvas rows per thread in the forward kernel
 constexpr int kRTileH = (kRThreads / kRTileW) * kRPPT;   // 32
 constexpr int kRMaxGroup = 8;
-constexpr int kBandPix = 1024;   // pixels per backward band
+constexpr int kBandPix = 1536;   // pixels per backward band (a 39x39 footprint fits one band)
 constexpr int kBandMaxW = 64;    // footprint columns per chunk
 constexpr int kBandMaxH = 256;   // footprint rows per band
 
@@ -330,13 +330,14 @@ template <int C>
 __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs p) {
     constexpr int NF4 = Tex<C>::NF4;
     constexpr int NCH = C + 2;
+    constexpr int NPG = (NCH == 3) ? 4 : NCH;   // stride of a per-pixel gradient record (float4 for C == 1)
     constexpr int QMAX = 4;   // texels owned per thread (G*G <= 1024)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = p.G, GG = G * G, GP = G + 2;
     // decoded texels with a one-texel zero border: zeros padding needs no tap masks
     float4* tex = reinterpret_cast<float4*>(smem_raw);                 // [GP*GP][NF4]
-    float* pixg = reinterpret_cast<float*>(tex + (size_t)GP * GP * NF4);   // [kBandPix][NCH] per-pixel gradients
-    float* col_fx = pixg + kBandPix * NCH;                             // [kBandMaxW] fractional sample position
+    float* pixg = reinterpret_cast<float*>(tex + (size_t)GP * GP * NF4);   // [kBandPix][NPG] per-pixel gradients
+    float* col_fx = pixg + kBandPix * NPG;                             // [kBandMaxW] fractional sample position
     float* col_bx = col_fx + kBandMaxW;                                // [kBandMaxW] normalised canvas coordinate
     int* col_x0 = reinterpret_cast<int*>(col_bx + kBandMaxW);          // [kBandMaxW] floor(sample position)
     float* row_fy = reinterpret_cast<float*>(col_x0 + kBandMaxW);      // [kBandMaxH]
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
     const float* lbase = p.logits + n * (size_t)(GG * (C + 1));
 
     // ---- 0. stage decoded texels (zero border) ----
+#pragma unroll 3
     for (int t = threadIdx.x; t < GP * GP; t += kRThreads) {
         const int yp = fast_div(t, inv_GP), xp = t - yp * GP;
         Tex<C> o;
@@ -400,9 +402,9 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
         const float inv_cw = 1.0f / (float)cw;
         // balanced bands of at most min(kBandPix / cw, kBandMaxH) rows
         const int n_rows = Yhi - Ylo + 1;
-        const int max_rows = min(kBandPix / cw, kBandMaxH);
-        const int n_bands = (n_rows + max_rows - 1) / max_rows;
-        const int rows_per_band = n_bands > 0 ? (n_rows + n_bands - 1) / n_bands : 1;
+        const int max_rows = min(fast_div(kBandPix, inv_cw), kBandMaxH);
+        const int n_bands = fast_div(n_rows + max_rows - 1, 1.0f / (float)max_rows);
+        const int rows_per_band = n_bands > 0 ? fast_div(n_rows + n_bands - 1, 1.0f / (float)n_bands) : 1;
         // ---- column tables of this chunk ----
         if (threadIdx.x < 32) { tcol_lo[threadIdx.x] = 1 << 30; tcol_hi[threadIdx.x] = -1; }
         __syncthreads();
@@ -447,6 +449,10 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) out[c] = 0.0f;
                 if (x0 != kOutside && y0 != kOutside) {
+                    const size_t pix = (size_t)(Yb + py) * p.Iw + (Xc + px);
+                    float gsv[C + 1];                                          // issued early: L2 latency overlaps the taps
+#pragma unroll
+                    for (int c = 0; c <= C; ++c) gsv[c] = __ldg(gs_b + (size_t)c * npix + pix);
                     const float wx1 = col_fx[px], wy1 = row_fy[py];
                     const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;       // == (x0+1) - ix, exactly
                     const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0), sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
@@ -465,17 +471,15 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
                             dvy[4 * q + e] = (a10[e] - a00[e]) * wx0 + (a11[e] - a01[e]) * wx1;
                         }
                     }
-                    const size_t pix = (size_t)(Yb + py) * p.Iw + (Xc + px);
                     const float a = v[C], m = v[C + 1] + 1e-9f;
                     float T = 0.0f;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const float g = __ldg(gs_b + (size_t)c * npix + pix);
-                        T = fmaf(g, v[c], T);
-                        out[c] = g * a * m;                                  // dL/dc~
+                        T = fmaf(gsv[c], v[c], T);
+                        out[c] = gsv[c] * a * m;                             // dL/dc~
                     }
                     out[C] = m * T;                                          // dL/da~
-                    out[C + 1] = a * T - __ldg(gs_b + (size_t)C * npix + pix);   // dL/dm~
+                    out[C + 1] = a * T - gsv[C];                             // dL/dm~
                     float gix = 0.0f, giy = 0.0f;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
@@ -488,8 +492,12 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
                     acc[2] = fmaf(dgx, col_bx[px], acc[2]);
                     acc[3] = fmaf(dgy, row_by[py], acc[3]);
                 }
+                if (NPG == 4) {
+                    *reinterpret_cast<float4*>(pixg + (size_t)pp * 4) = make_float4(out[0], out[1], out[2], 0.0f);
+                } else {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) pixg[(size_t)pp * NCH + c] = out[c];
+                    for (int c = 0; c < NCH; ++c) pixg[(size_t)pp * NPG + c] = out[c];
+                }
             }
             __syncthreads();
             // ---- 2. texels gather through the transposed bilinear weights (exact ranges) ----
@@ -501,12 +509,19 @@ __global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs 
                 for (int py = pya; py <= pyb; ++py) {
                     const float fy = row_fy[py];
                     const float wy = (row_y0[py] == ti) ? 1.0f - fy : fy;
-                    const float* grow = pixg + (size_t)py * cw * NCH;
+                    const float* grow = pixg + (size_t)py * cw * NPG;
                     for (int px = pxa; px <= pxb; ++px) {
                         const float fx = col_fx[px];
                         const float w = wy * ((col_x0[px] == tj) ? 1.0f - fx : fx);
+                        if (NPG == 4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(grow + px * 4);
+                            dT[q][0] = fmaf(w, g4.x, dT[q][0]);
+                            dT[q][1] = fmaf(w, g4.y, dT[q][1]);
+                            dT[q][2] = fmaf(w, g4.z, dT[q][2]);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) dT[q][c] = fmaf(w, grow[px * NCH + c], dT[q][c]);
+                            for (int c = 0; c < NCH; ++c) dT[q][c] = fmaf(w, grow[px * NPG + c], dT[q][c]);
+                        }
                     }
                 }
             }
@@ -566,7 +581,7 @@ static int launch_fwd(const RenderArgs& a, cudaStream_t st) {
     RenderArgs p = a;
     const int slot_f4 = p.G * p.G * Tex<C>::NF4;
     const size_t slot_bytes = (size_t)slot_f4 * sizeof(float4);
-    int group = (int)((64 * 1024) / slot_bytes);
+    int group = (int)((48 * 1024) / slot_bytes);
     if (group > kRMaxGroup) group = kRMaxGroup;
     if (group < 1) group = 1;
     p.group = group;
@@ -594,7 +609,7 @@ static int launch_bwd(const RenderBwdArgs& p, const float* recon, const float* d
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const size_t smem = (size_t)(p.G + 2) * (p.G + 2) * Tex<C>::NF4 * sizeof(float4) +
-                        sizeof(float) * ((size_t)kBandPix * (C + 2) + 3 * kBandMaxW + 3 * kBandMaxH + 4 * 32);
+                        sizeof(float) * ((size_t)kBandPix * ((C + 2) == 3 ? 4 : (C + 2)) + 3 * kBandMaxW + 3 * kBandMaxH + 4 * 32);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
     static size_t smem_set = 0;
     if (smem > smem_set) {
