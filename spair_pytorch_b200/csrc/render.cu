@@ -327,7 +327,7 @@ struct RenderBwdArgs {
 constexpr int kOutside = -1000000;   // marks a footprint column / row whose sample falls outside the texture
 
 template <int C>
-__global__ void __launch_bounds__(kRThreads, 3) render_bwd_kernel(RenderBwdArgs p) {
+__global__ void __launch_bounds__(kRThreads, (C <= 2) ? 4 : 3) render_bwd_kernel(RenderBwdArgs p) {
     constexpr int NF4 = Tex<C>::NF4;
     constexpr int NCH = C + 2;
     constexpr int NPG = (NCH == 3) ? 4 : NCH;   // stride of a per-pixel gradient record (float4 for C == 1)
