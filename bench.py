@@ -181,8 +181,15 @@ def kernel_roofline(net, x, steps=20):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "bytes": nbytes, "achieved": gbs, "frac": gbs / peak}
     dom = max(out, key=lambda k: out[k]["ms"])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+    # kernels at this shape (profiles/r01_warp_kernels_final_full.md; B=256, C=1, I=128, 121 cells, G=28)
+    ncu_traffic = {"render_bwd": 228623872 + 159112192, "render_fwd": 201631488 + 24653056,
+                   "glimpse_fwd": 17969920 + 44048128, "glimpse_bwd": 115137792 + 4571392}
+    traffic = ncu_traffic.get(dom) if (B, C, I, HW, G) == (256, 1, 128, 121, 28) else None
     roof = {"bound": "hbm", "kernel": dom, "achieved": out[dom]["achieved"], "peak": peak, "unit": "GB/s",
-            "frac": out[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": out[dom]["frac"], "traffic": traffic,
+            "traffic_source": "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)" if traffic else None,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": out[dom]["bytes"], "ms_per_launch": out[dom]["ms"],
             "timing": "CUDA events on the launching stream, 256 MB L2 flush between launches, mean of %d" % steps}
     return roof, out
@@ -308,7 +315,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -362,11 +369,34 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return line
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything that writes to fd 1 (NCCL's version banner, stray prints of libraries) to stderr and
+    keep the real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -385,9 +415,7 @@ def main():
         # convenience: re-launch under torchrun when asked for N > 1 from a plain `python bench.py`
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
-    with contextlib.redirect_stdout(sys.stderr):   # keep stdout for the JSON line only
-        pass
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_ours(args)
 
 

@@ -69,3 +69,37 @@ class ScatteredSpritesDataset(data.Dataset):
 
     def __len__(self):
         return self.length
+
+
+def scattered_sprites_gpu(batch, image_shape, device, generator=None, max_sprites=9, sprite_px=(10, 20)):
+    """Device-side scene generator (no host work, no H2D copy): the same family of scenes as
+    ``scattered_sprites`` — ``k ~ U{1..max}`` glyph-like unions of 2-4 Gaussian strokes inside a random
+    square, max-composited on black — built with batched tensor ops on ``device``.
+    Returns (image [B,C,H,W] in [0,1], bbox [B,max_sprites,4] as (x,y,w,h) px, count [B,1])."""
+    C, H, W = image_shape
+    S, K = max_sprites, 4
+    kw = dict(device=device, generator=generator)
+    count = torch.randint(1, S + 1, (batch, 1), **kw)
+    size = torch.randint(sprite_px[0], min(sprite_px[1], H, W) + 1, (batch, S), **kw).float()
+    x0 = torch.floor(torch.rand(batch, S, **kw) * (W - size + 1))
+    y0 = torch.floor(torch.rand(batch, S, **kw) * (H - size + 1))
+    live = (torch.arange(S, device=device)[None, :] < count).float()                       # [B,S]
+    n_strokes = torch.randint(2, 5, (batch, S, 1), **kw)
+    stroke_on = (torch.arange(K, device=device)[None, None, :] < n_strokes).float()        # [B,S,K]
+    cy, cx = (0.2 + 0.6 * torch.rand(batch, S, K, **kw) for _ in range(2))
+    rad = 0.08 + 0.22 * torch.rand(batch, S, K, **kw)
+    ys = torch.arange(H, device=device).float()[None, None, :, None]                       # [1,1,H,1]
+    xs = torch.arange(W, device=device).float()[None, None, None, :]                       # [1,1,1,W]
+    u = (xs - x0[..., None, None]) / (size[..., None, None] - 1).clamp(min=1)              # sprite-local coords [B,S,1,W]
+    v = (ys - y0[..., None, None]) / (size[..., None, None] - 1).clamp(min=1)              # [B,S,H,1]
+    inside = ((u >= 0) & (u <= 1)).float() * ((v >= 0) & (v <= 1)).float() * live[..., None, None]   # [B,S,H,W]
+    sprite = torch.zeros(batch, S, H, W, device=device)
+    for k in range(K):
+        d2 = (u - cx[..., k, None, None]) ** 2 + (v - cy[..., k, None, None]) ** 2
+        blob = torch.exp(-d2 / (2 * rad[..., k, None, None] ** 2)) * stroke_on[..., k, None, None]
+        sprite = torch.maximum(sprite, blob)
+    sprite = (sprite * 1.2).clamp(0, 1) * inside
+    colour = torch.ones(batch, S, C, device=device) if C == 1 else 0.3 + 0.7 * torch.rand(batch, S, C, **kw)
+    image = (sprite[:, :, None] * colour[..., None, None]).amax(dim=1)                     # max-composite -> [B,C,H,W]
+    bbox = torch.stack([x0, y0, size, size], dim=-1) * live[..., None]
+    return image, bbox, count.float()

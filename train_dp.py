@@ -31,7 +31,7 @@ from torch.utils import data as torch_data
 
 from spair import config as cfg
 from spair import metric
-from spair.dataloader import ScatteredSpritesDataset, SimpleScatteredMNISTDataset
+from spair.dataloader import SimpleScatteredMNISTDataset, scattered_sprites_gpu
 from spair.models import SPAIR
 from spair_pytorch_b200 import dp
 from spair_pytorch_b200.graphed import GraphedTrainStep
@@ -89,22 +89,27 @@ def main():
         if rank == 0:
             print("resumed from step", ck["step"])
 
-    dataset = SimpleScatteredMNISTDataset(args.hdf5) if args.hdf5 else \
-        ScatteredSpritesDataset(length=1 << 20, image_shape=cfg.INPUT_IMAGE_SHAPE, seed=1234 + 7919 * rank)
-    loader = torch_data.DataLoader(dataset, batch_size=args.batch, pin_memory=True, num_workers=2, drop_last=True,
-                                   sampler=None if not args.hdf5 else torch_data.distributed.DistributedSampler(
-                                       dataset, world, rank) if world > 1 else None)
+    loader = None
+    if args.hdf5:                                                 # the reference's dataset, one DataLoader per rank
+        dataset = SimpleScatteredMNISTDataset(args.hdf5)
+        sampler = torch_data.distributed.DistributedSampler(dataset, world, rank) if world > 1 else None
+        loader = torch_data.DataLoader(dataset, batch_size=args.batch, pin_memory=True, num_workers=2, drop_last=True,
+                                       sampler=sampler)
+        it = iter(loader)
+    data_gen = torch.Generator(device=dev).manual_seed(1234 + 7919 * rank)    # procedural scenes made on the device
     torch.manual_seed(1000 + rank)                                # per-rank noise stream
     gstep, t0, seen = None, time.time(), 0
-    it = iter(loader)
     last = step + args.steps
     while step < last:
-        try:
-            x_image, y_bbox, y_count = next(it)
-        except StopIteration:
-            it = iter(loader)
-            continue
-        x_image = x_image.float()
+        if loader is not None:
+            try:
+                x_image, y_bbox, y_count = next(it)
+            except StopIteration:
+                it = iter(loader)
+                continue
+            x_image = x_image.float()
+        else:
+            x_image, y_bbox, y_count = scattered_sprites_gpu(args.batch, cfg.INPUT_IMAGE_SHAPE, dev, data_gen)
         if args.eager:
             out = ddp.step(x_image.to(dev, non_blocking=True), step)
         else:
