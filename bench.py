@@ -285,6 +285,9 @@ def run_ours(args):
         n_launch = K.launch_count() - n0 if launches_per_step is None else launches_per_step * steps
         return float(ms) / steps, n_launch, clk.summary()
 
+    if args.profile_step:       # for `ncu`: warm-up + the timed steps only (no e2e pass, no kernel microbench, no JSON)
+        timed(step_resident, args.steps, args.warmup)
+        return None
     ms_res, launches, clocks = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     value = world * B / (ms_res * 1e-3)
@@ -405,6 +408,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--profile-step", action="store_true", help="run warm-up + timed steps only and print nothing (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -240,6 +240,51 @@ int spair_kl_bwd(const float* dmean, const float* dstd, const float* pres,
                  const float* p_z, const float* d_sums /* [B,7] */, int B, int HW, int A,
                  float* d_dmean, float* d_dstd, float* d_pres, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * L0-L4 + G fused: the WHOLE forward cell sweep (models.py:68-117) in one persistent launch.
+ * The sweep is partitioned by image (all dependencies of a cell are cells of the same image): a CTA
+ * owns `ipc` images and walks every wavefront with block-level barriers only.  It performs, per
+ * wavefront, exactly what spair_context_gather_fwd -> box MLP -> spair_box_head_fwd ->
+ * spair_glimpse_fwd -> encoder MLP -> spair_normal_head_fwd (attr) -> z MLP ->
+ * spair_normal_head_fwd (depth) -> obj MLP -> spair_pres_head_fwd do, and fills the same
+ * wavefront-major activation buffers (x, h0, h1, y of each MLP; row = position(cell)*B + b), so the
+ * backward pass is unchanged.  The MLPs (reference modules.py:124-165: two ReLU hidden layers + a
+ * linear output, multi-head outputs concatenated) are evaluated by the kernel itself in fp32 SIMT
+ * FMAs from TRANSPOSED weights wt[k][n].  Limits: max_cells * ipc <= spair_sweep_max_rows(),
+ * layer widths <= 256, G <= 64.
+ * ---------------------------------------------------------------------------------- */
+typedef struct spair_sweep_dims {
+    int B, HW, Hc, Wc;      /* batch, cells */
+    int F, A, P;            /* backbone features, attribute dims, passthrough features */
+    int C, Ih, Iw, G;       /* image channels / size, glimpse side */
+    int ipc;                /* images per CTA */
+    int n_wavefronts, max_cells, n_nb;
+} spair_sweep_dims;
+
+typedef struct spair_sweep_mlp {
+    const float* wt[3];     /* transposed weights [k][n] of hidden0, hidden1, output */
+    const float* b[3];      /* biases [n] */
+    int k[3], n[3];
+    float* x; int ld_x;     /* [HW*B, ld_x] input rows; the kernel fills them */
+    float* h0; float* h1;   /* [HW*B, n[0]], [HW*B, n[1]] post-ReLU activations (written) */
+    float* y;               /* [HW*B, n[2]] outputs (written) */
+} spair_sweep_mlp;
+
+int spair_sweep_max_rows(void);
+
+int spair_sweep_fwd(const spair_sweep_dims* dims,        /* host */
+                    const int* order,                    /* [HW] cells in wavefront-major order (device) */
+                    const int* starts,                   /* [n_wavefronts+1] (device) */
+                    const int* nb_offsets,               /* host: n_nb pairs (dh,dw) */
+                    const float* image, const float* feat, const float* edge,
+                    const float* eps_where, const float* eps_attr, const float* eps_depth, const float* u_pres,
+                    const spair_box_geom* geom,          /* host */
+                    const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                    const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp,   /* host structs, device pointers inside */
+                    float* box, float* z_where, float* attr, float* depth, float* pres,
+                    float* dmean, float* dstd,           /* image-major outputs */
+                    void* stream);
+
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
 

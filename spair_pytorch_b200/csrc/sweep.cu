@@ -1,0 +1,382 @@
+// Fused forward sweep: the whole autoregressive cell loop (reference models.py:68-117) in ONE persistent launch.
+//
+// Every per-cell computation of an image depends only on that image (the lateral context reads cells of the SAME
+// image), so the sweep is partitioned by image: a CTA owns `ipc` images and walks all Wc+2(Hc-1) wavefronts for
+// them with block-level barriers only — no kernel boundary, no grid-wide synchronisation.  Per wavefront a CTA
+// handles R = n_cells * ipc <= 16 rows through context gather -> box MLP -> box head -> glimpse -> encoder MLP ->
+// attr head -> z MLP -> depth head -> obj MLP -> presence head.  The MLP layers are register-tiled SIMT dot
+// products: a thread owns one output column (and 8 or 16 rows), streams the TRANSPOSED weights Wt[k][n] from L2
+// with coalesced loads and reads the activations as 128-bit shared-memory broadcasts; each weight element is
+// fetched once per CTA and wavefront and reused for all rows.  All activations are also written to the same
+// wavefront-major global buffers the unfused path uses, so the backward pass (and the weight-gradient GEMMs) are
+// unchanged.  This replaces ~27 launches per wavefront (12 cuBLAS GEMMs of <= 1536 rows, 8 elementwise, 6 head
+// kernels) whose issue-to-issue latency, not their arithmetic, bounded the step.
+#include "warp_math.cuh"
+
+namespace spair {
+
+constexpr int kSwThreads = 512;     // 16 warps: the weight stream from L2 is latency bound, warps hide it
+constexpr int kSwRows = 16;        // padded rows per CTA and wavefront
+constexpr int kSwKC = 128;         // K-chunk of a layer whose input comes from global memory
+constexpr int kSwKCP = kSwKC + 4;  // padded chunk row (keeps float4 alignment, staggers banks)
+constexpr int kSwHP = 256 + 4;     // padded hidden row
+constexpr int kSwMaxG = 64;
+
+struct SweepLayer {
+    const float* Wt;   // [K][N] transposed weight
+    const float* b;    // [N]
+    int K, N;
+};
+
+struct SweepMLP {
+    SweepLayer l[3];
+    float* X; int ldX;     // [HW*B, ldX] input rows (wavefront-major)
+    float* H0; float* H1;  // [HW*B, N0], [HW*B, N1] post-ReLU activations
+    float* Y;              // [HW*B, N2]
+};
+
+struct SweepFwdArgs {
+    int B, HW, Hc, Wc, F, A, P, C, Ih, Iw, G, ipc, n_wavefronts;
+    NeighbourList nb;
+    const int* order;      // [HW] cells in wavefront-major order
+    const int* starts;     // [n_wavefronts + 1]
+    const float* image; const float* feat; const float* edge;
+    const float* eps_where; const float* eps_attr; const float* eps_depth; const float* u_pres;
+    spair_box_geom geom;
+    SweepMLP box, enc, z, obj;
+    float* out_box; float* z_where; float* attr; float* depth; float* pres; float* dmean; float* dstd;
+};
+
+// ---- one dense layer over the CTA's rows -----------------------------------------------------------------------
+// in_smem != nullptr : input activations resident in shared memory, in_smem[r * kSwHP + k]
+// otherwise          : input rows in global memory X[grow[r] * ldX + k], staged through `chunk` in K-chunks
+// out_smem[r * kSwHP + n] receives the result (ReLU applied if relu), out_glob[grow[r] * N + n] as well.
+template <int RG>
+__device__ __forceinline__ void fma_rows4(float (&acc)[RG], const float* __restrict__ xp, int xs_stride, const float* w) {
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(xp + r * xs_stride);
+        acc[r] = fmaf(w[0], x.x, acc[r]);
+        acc[r] = fmaf(w[1], x.y, acc[r]);
+        acc[r] = fmaf(w[2], x.z, acc[r]);
+        acc[r] = fmaf(w[3], x.w, acc[r]);
+    }
+}
+
+// acc[r] += sum_k Wt[k0 + k][n] * xs[row0 + r][k] for k in [0, kc), kc a multiple of 4 (xs zero-padded), weights
+// beyond K treated as 0.  Main loop: 8 unguarded coalesced weight loads issued before use, unrolled twice, so ~16
+// L2 requests per thread are in flight (the layer streams its weights once per CTA and wavefront).
+template <int RG>
+__device__ __forceinline__ void dense_accumulate(float (&acc)[RG], const float* __restrict__ Wt, int N, int n, int k0,
+                                                 int kc, int K, const float* __restrict__ xs, int xs_stride, int row0) {
+    const float* wp = Wt + k0 * N + n;
+    const float* xp = xs + row0 * xs_stride;
+    const int k_real = min(kc, K - k0);
+    const int k_main = k_real & ~7;
+    int k = 0;
+#pragma unroll 2
+    for (; k < k_main; k += 8) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ldg(wp + i * N);
+        wp += 8 * N;
+        fma_rows4<RG>(acc, xp + k, xs_stride, w);
+        fma_rows4<RG>(acc, xp + k + 4, xs_stride, w + 4);
+    }
+    for (; k < kc; k += 4) {
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = (k + i < k_real) ? __ldg(wp + i * N) : 0.0f;
+        wp += 4 * N;
+        fma_rows4<RG>(acc, xp + k, xs_stride, w);
+    }
+}
+
+template <int RG>
+__device__ void dense_layer_rg(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
+                               const int* __restrict__ grow, int nrows, float* chunk, float* out_smem,
+                               float* __restrict__ out_glob, bool relu) {
+    constexpr int NCOLP = kSwThreads * RG / kSwRows;      // threads = NCOLP columns x (kSwRows / RG) row groups
+    const int n = threadIdx.x % NCOLP;
+    const int row0 = (threadIdx.x / NCOLP) * RG;
+    const bool active = n < L.N && row0 < nrows;       // a row group made of padding rows only has nothing to do
+    float acc[RG];
+    const float bias = active ? __ldg(L.b + n) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < RG; ++r) acc[r] = bias;
+    if (in_smem) {
+        const int kc = (L.K + 3) & ~3;      // hidden rows are zero-padded to a multiple of 4
+        if (active) dense_accumulate<RG>(acc, L.Wt, L.N, n, 0, kc, L.K, in_smem, kSwHP, row0);
+    } else {
+        for (int k0 = 0; k0 < L.K; k0 += kSwKC) {
+            const int kc = min(kSwKC, L.K - k0);
+            const int kcp = (kc + 3) & ~3;
+            __syncthreads();                 // previous chunk fully consumed
+            for (int idx = threadIdx.x; idx < kSwRows * kcp; idx += kSwThreads) {
+                const int r = idx / kcp, kk = idx - r * kcp;
+                chunk[r * kSwKCP + kk] = (r < nrows && kk < kc) ? Xg[(size_t)grow[r] * ldX + k0 + kk] : 0.0f;
+            }
+            __syncthreads();
+            if (active) dense_accumulate<RG>(acc, L.Wt, L.N, n, k0, kcp, L.K, chunk, kSwKCP, row0);
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            const float v = relu ? fmaxf(acc[r], 0.0f) : acc[r];
+            const int row = row0 + r;
+            out_smem[row * kSwHP + n] = v;
+            if (row < nrows) out_glob[(size_t)grow[row] * L.N + n] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in_smem, const float* Xg, int ldX,
+                                            const int* grow, int nrows, float* chunk, float* out_smem, float* out_glob,
+                                            bool relu) {
+    // zero the padding columns the next layer's float4 reads may touch
+    for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + L.N + (idx & 3)] = 0.0f;
+    if (L.N <= 128) dense_layer_rg<4>(L, in_smem, Xg, ldX, grow, nrows, chunk, out_smem, out_glob, relu);     // 128 x 4
+    else dense_layer_rg<8>(L, in_smem, Xg, ldX, grow, nrows, chunk, out_smem, out_glob, relu);                // 256 x 2
+    __syncthreads();
+}
+
+// three-layer MLP: X (global) -> H0 -> H1 -> Y ; result left in shared memory `y`
+__device__ __forceinline__ void mlp3(const SweepMLP& M, const int* grow, int nrows, float* chunk, float* ha, float* hb,
+                                     float* y) {
+    dense_layer(M.l[0], nullptr, M.X, M.ldX, grow, nrows, chunk, ha, M.H0, true);
+    dense_layer(M.l[1], ha, nullptr, 0, grow, nrows, chunk, hb, M.H1, true);
+    dense_layer(M.l[2], hb, nullptr, 0, grow, nrows, chunk, y, M.Y, false);
+}
+
+__device__ __forceinline__ int sw_box_slot(int k) { return k == 0 ? 1 : (k == 1 ? 0 : (k == 2 ? 3 : 2)); }
+
+__global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p) {
+    static_assert(kSwThreads * 4 / kSwRows == 128 && kSwThreads * 8 / kSwRows == 256, "thread mapping of dense_layer_rg");
+    extern __shared__ __align__(16) float sm[];
+    float* chunk = sm;                                  // [kSwRows][kSwKCP]
+    float* ha = chunk + kSwRows * kSwKCP;               // [kSwRows][kSwHP]
+    float* hb = ha + kSwRows * kSwHP;
+    float* y = hb + kSwRows * kSwHP;
+    float* base_g = y + kSwRows * kSwHP;                // [kSwMaxG] normalised base grid of the glimpse
+    float* zw_s = base_g + kSwMaxG;                     // [kSwRows][4] boxes of the current rows
+    int* grow = reinterpret_cast<int*>(zw_s + kSwRows * 4);   // [kSwRows] global row of each local row
+    int* rcell = grow + kSwRows;                        // [kSwRows] cell id
+    int* rimg = rcell + kSwRows;                        // [kSwRows] image
+
+    const int b0 = blockIdx.x * p.ipc;
+    const int n_img = min(p.ipc, p.B - b0);
+    if (n_img <= 0) return;
+    const int E = p.A + 6, D = 4 + p.A + 1;
+    const int CTX = p.nb.n * E;
+    const int c_pt = p.F + CTX, c_box = c_pt + p.P, c_attr = c_box + 4, c_depth = c_attr + p.A;
+    const int GG = p.G * p.G;
+    for (int j = threadIdx.x; j < p.G; j += kSwThreads) base_g[j] = base_coord(j, p.G);
+
+    for (int t = 0; t < p.n_wavefronts; ++t) {
+        const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
+        const int nrows = n_cells * n_img;
+        __syncthreads();                                // previous wavefront's latents are visible; row tables free
+        if (threadIdx.x < kSwRows) {
+            const int r = threadIdx.x;
+            if (r < nrows) {
+                const int k = r / n_img, li = r - k * n_img;
+                grow[r] = (s0 + k) * p.B + b0 + li;
+                rcell[r] = p.order[s0 + k];
+                rimg[r] = b0 + li;
+            } else {
+                grow[r] = 0; rcell[r] = 0; rimg[r] = b0;
+            }
+        }
+        __syncthreads();
+
+        // ---- L0: lateral context -> input columns [0, F+CTX) of the three networks (models.py:73,76) ----
+        const int width = p.F + CTX;
+        for (int idx = threadIdx.x; idx < nrows * width; idx += kSwThreads) {
+            const int r = idx / width, col = idx - r * width;
+            const int b = rimg[r], cell = rcell[r];
+            const int h = cell / p.Wc, w = cell - h * p.Wc;
+            float v;
+            if (col < p.F) {
+                v = __ldg(p.feat + ((size_t)(b * p.F + col) * p.Hc + h) * p.Wc + w);
+            } else {
+                const int s = (col - p.F) / E, j = (col - p.F) - s * E;
+                const int nh = h + p.nb.dh[s], nw = w + p.nb.dw[s];
+                if (nh >= 0 && nh < p.Hc && nw >= 0 && nw < p.Wc) {
+                    const size_t o = (size_t)b * p.HW + nh * p.Wc + nw;   // written by this CTA in an earlier wavefront
+                    if (j < 4) v = p.out_box[o * 4 + j];
+                    else if (j < 4 + p.A) v = p.attr[o * p.A + (j - 4)];
+                    else if (j == 4 + p.A) v = p.depth[o];
+                    else v = p.pres[o];
+                } else {
+                    v = __ldg(p.edge + j);
+                }
+            }
+            const size_t g = grow[r];
+            p.box.X[g * p.box.ldX + col] = v;
+            p.z.X[g * p.z.ldX + col] = v;
+            p.obj.X[g * p.obj.ldX + col] = v;
+        }
+        // (dense_layer starts with a barrier before it reads the rows back)
+
+        // ---- z_where: box network + box head (models.py:76-79, 322-381) ----
+        mlp3(p.box, grow, nrows, chunk, ha, hb, y);
+        for (int idx = threadIdx.x; idx < nrows * (4 + p.P); idx += kSwThreads) {
+            const int r = idx / (4 + p.P), k = idx - r * (4 + p.P);
+            const size_t g = grow[r];
+            const float* yr = y + r * kSwHP;
+            if (k >= 4) {
+                p.z.X[g * p.z.ldX + c_pt + (k - 4)] = yr[8 + (k - 4)];
+                continue;
+            }
+            const int cell = rcell[r];
+            const size_t o = (size_t)rimg[r] * p.HW + cell;
+            const float mean = yr[k];
+            const float std_ = sigmoid_f(clamp10(yr[4 + k])) * 2.0f;
+            const float zl = mean + __ldg(p.eps_where + o * 4 + k) * std_;
+            const float sg = sigmoid_f(clamp10(zl));
+            float bval, zval;
+            if (k < 2) {
+                bval = p.geom.yx_scale * sg + p.geom.yx_min;
+                const float pos = (k == 0) ? (float)(cell / p.Wc) : (float)(cell % p.Wc);
+                zval = (k == 0 ? p.geom.cell_ratio_y : p.geom.cell_ratio_x) * (bval + pos);
+            } else {
+                bval = p.geom.hw_scale * sg + p.geom.hw_min;
+                zval = bval * p.geom.anchor / (k == 2 ? p.geom.img_h : p.geom.img_w);
+            }
+            const int slot = sw_box_slot(k);
+            p.out_box[o * 4 + slot] = bval;
+            p.z_where[o * 4 + slot] = zval;
+            zw_s[r * 4 + slot] = zval;
+            p.dmean[o * D + k] = mean;
+            p.dstd[o * D + k] = std_;
+            p.z.X[g * p.z.ldX + c_box + slot] = bval;
+            p.obj.X[g * p.obj.ldX + c_box + slot] = bval;
+        }
+        __syncthreads();
+
+        // ---- z_what: glimpse (modules.py:216-273, border padding) -> encoder input rows ----
+        for (int idx = threadIdx.x; idx < nrows * GG; idx += kSwThreads) {
+            const int r = idx / GG, tt = idx - r * GG;
+            const int i = tt / p.G, j = tt - i * p.G;
+            const FwdAffine A(zw_s[r * 4 + 0], zw_s[r * 4 + 1], zw_s[r * 4 + 2], zw_s[r * 4 + 3]);
+            float ix = unnormalize(affine_coord(base_g[j], A.ax, A.cx), 0.5f * (float)p.Iw);
+            float iy = unnormalize(affine_coord(base_g[i], A.ay, A.cy), 0.5f * (float)p.Ih);
+            ix = fminf(fmaxf(ix, 0.0f), (float)(p.Iw - 1));
+            iy = fminf(fmaxf(iy, 0.0f), (float)(p.Ih - 1));
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            const int x1 = min(x0 + 1, p.Iw - 1), y1 = min(y0 + 1, p.Ih - 1);     // weight is exactly 0 when clamped
+            const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+            const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0), sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
+            float* orow = p.enc.X + (size_t)grow[r] * p.enc.ldX;
+            for (int c = 0; c < p.C; ++c) {
+                const float* pl = p.image + ((size_t)rimg[r] * p.C + c) * p.Ih * p.Iw;
+                float acc = __fmul_rn(__ldg(pl + (size_t)y0 * p.Iw + x0), nw);
+                acc = fmaf(__ldg(pl + (size_t)y0 * p.Iw + x1), ne, acc);
+                acc = fmaf(__ldg(pl + (size_t)y1 * p.Iw + x0), sw, acc);
+                acc = fmaf(__ldg(pl + (size_t)y1 * p.Iw + x1), se, acc);
+                orow[c * GG + tt] = acc;
+            }
+        }
+        mlp3(p.enc, grow, nrows, chunk, ha, hb, y);
+        for (int idx = threadIdx.x; idx < nrows * p.A; idx += kSwThreads) {
+            const int r = idx / p.A, k = idx - r * p.A;
+            const size_t g = grow[r];
+            const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+            const float* yr = y + r * kSwHP;
+            const float mean = yr[k];
+            const float std_ = sigmoid_f(clamp10(yr[p.A + k])) * 2.0f;
+            const float zv = mean + __ldg(p.eps_attr + o * p.A + k) * std_;
+            p.attr[o * p.A + k] = zv;
+            p.dmean[o * D + 4 + k] = mean;
+            p.dstd[o * D + 4 + k] = std_;
+            p.z.X[g * p.z.ldX + c_attr + k] = zv;
+            p.obj.X[g * p.obj.ldX + c_attr + k] = zv;
+        }
+
+        // ---- z_depth (models.py:88-97) ----
+        mlp3(p.z, grow, nrows, chunk, ha, hb, y);
+        for (int idx = threadIdx.x; idx < nrows * (1 + p.P); idx += kSwThreads) {
+            const int r = idx / (1 + p.P), k = idx - r * (1 + p.P);
+            const size_t g = grow[r];
+            const float* yr = y + r * kSwHP;
+            if (k >= 1) {
+                p.obj.X[g * p.obj.ldX + c_pt + (k - 1)] = yr[2 + (k - 1)];
+                continue;
+            }
+            const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+            const float mean = yr[0];
+            const float std_ = sigmoid_f(clamp10(yr[1])) * 2.0f;
+            const float zv = 4.0f * sigmoid_f(clamp10(mean + __ldg(p.eps_depth + o) * std_));
+            p.depth[o] = zv;
+            p.dmean[o * D + D - 1] = mean;
+            p.dstd[o * D + D - 1] = std_;
+            p.obj.X[g * p.obj.ldX + c_depth] = zv;
+        }
+
+        // ---- z_pres (models.py:100-105, 393-411) ----
+        mlp3(p.obj, grow, nrows, chunk, ha, hb, y);
+        if (threadIdx.x < nrows) {
+            const int r = threadIdx.x;
+            const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+            const float u = __ldg(p.u_pres + o);
+            const float noise = logf(u + 10e-10f) - logf(1.0f - u + 10e-10f);
+            p.pres[o] = sigmoid_f(clamp10(y[r * kSwHP]) + noise);
+        }
+    }
+}
+
+}  // namespace spair
+
+using namespace spair;
+
+// Host-side description of one MLP for spair_sweep_fwd (mirrors the C struct in include/spair_b200.h)
+static bool to_mlp(const spair_sweep_mlp* m, SweepMLP& out) {
+    if (!m || !m->x || !m->h0 || !m->h1 || !m->y) return false;
+    for (int i = 0; i < 3; ++i) {
+        if (!m->wt[i] || !m->b[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
+        out.l[i] = SweepLayer{m->wt[i], m->b[i], m->k[i], m->n[i]};
+    }
+    if (m->k[1] != m->n[0] || m->k[2] != m->n[1] || m->ld_x < m->k[0]) return false;
+    out.X = m->x; out.ldX = m->ld_x; out.H0 = m->h0; out.H1 = m->h1; out.Y = m->y;
+    return true;
+}
+
+extern "C" int spair_sweep_max_rows(void) { return kSwRows; }
+
+extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
+                               const float* image, const float* feat, const float* edge, const float* eps_where,
+                               const float* eps_attr, const float* eps_depth, const float* u_pres,
+                               const spair_box_geom* geom, const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                               const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp, float* box, float* z_where,
+                               float* attr, float* depth, float* pres, float* dmean, float* dstd, void* stream) {
+    SPAIR_REQUIRE(d && order && starts && nb_offsets && image && feat && edge && eps_where && eps_attr && eps_depth && u_pres);
+    SPAIR_REQUIRE(geom && box && z_where && attr && depth && pres && dmean && dstd);
+    SPAIR_REQUIRE(d->B > 0 && d->HW == d->Hc * d->Wc && d->G > 0 && d->G <= kSwMaxG && d->ipc >= 1 && d->n_wavefronts > 0);
+    SPAIR_REQUIRE(d->max_cells * d->ipc <= kSwRows && d->n_nb >= 1 && d->n_nb <= SPAIR_MAX_NEIGHBOURS);
+    SweepFwdArgs a;
+    a.B = d->B; a.HW = d->HW; a.Hc = d->Hc; a.Wc = d->Wc; a.F = d->F; a.A = d->A; a.P = d->P; a.C = d->C;
+    a.Ih = d->Ih; a.Iw = d->Iw; a.G = d->G; a.ipc = d->ipc; a.n_wavefronts = d->n_wavefronts;
+    a.nb.n = d->n_nb;
+    for (int i = 0; i < d->n_nb; ++i) { a.nb.dh[i] = nb_offsets[2 * i]; a.nb.dw[i] = nb_offsets[2 * i + 1]; }
+    a.order = order; a.starts = starts; a.image = image; a.feat = feat; a.edge = edge;
+    a.eps_where = eps_where; a.eps_attr = eps_attr; a.eps_depth = eps_depth; a.u_pres = u_pres; a.geom = *geom;
+    SPAIR_REQUIRE(to_mlp(box_mlp, a.box) && to_mlp(enc_mlp, a.enc) && to_mlp(z_mlp, a.z) && to_mlp(obj_mlp, a.obj));
+    const int E = d->A + 6, CTX = d->n_nb * E;
+    SPAIR_REQUIRE(a.box.l[0].K == d->F + CTX && a.box.l[2].N == 8 + d->P);
+    SPAIR_REQUIRE(a.enc.l[0].K == d->C * d->G * d->G && a.enc.l[2].N == 2 * d->A);
+    SPAIR_REQUIRE(a.z.l[0].K == d->F + CTX + d->P + 4 + d->A && a.z.l[2].N == 2 + d->P);
+    SPAIR_REQUIRE(a.obj.l[0].K == a.z.l[0].K + 1 && a.obj.l[2].N == 1);
+    a.out_box = box; a.z_where = z_where; a.attr = attr; a.depth = depth; a.pres = pres; a.dmean = dmean; a.dstd = dstd;
+    const size_t smem = sizeof(float) * (size_t)(kSwRows * kSwKCP + 3 * kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
+                        sizeof(int) * 3 * kSwRows;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sweep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int grid = (d->B + d->ipc - 1) / d->ipc;
+    sweep_fwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
+    SPAIR_LAUNCH_CHECK();
+}

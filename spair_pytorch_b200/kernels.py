@@ -27,6 +27,19 @@ class BoxGeom(ctypes.Structure):
                 ("yx_scale", "yx_min", "hw_scale", "hw_min", "anchor", "img_h", "img_w", "cell_ratio_y", "cell_ratio_x")]
 
 
+class SweepDims(ctypes.Structure):
+    """``spair_sweep_dims`` of include/spair_b200.h."""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("B", "HW", "Hc", "Wc", "F", "A", "P", "C", "Ih", "Iw", "G", "ipc", "n_wavefronts", "max_cells", "n_nb")]
+
+
+class SweepMLP(ctypes.Structure):
+    """``spair_sweep_mlp`` of include/spair_b200.h."""
+    _fields_ = [("wt", ctypes.c_void_p * 3), ("b", ctypes.c_void_p * 3), ("k", ctypes.c_int * 3), ("n", ctypes.c_int * 3),
+                ("x", ctypes.c_void_p), ("ld_x", ctypes.c_int), ("h0", ctypes.c_void_p), ("h1", ctypes.c_void_p),
+                ("y", ctypes.c_void_p)]
+
+
 class SpairKernelError(RuntimeError):
     pass
 
@@ -55,6 +68,8 @@ _SIGNATURES = {
     "spair_kl_fwd": [_P] * 6 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
+    "spair_sweep_max_rows": [],
+    "spair_sweep_fwd": [_P] * 23 + [_P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -98,7 +113,7 @@ def base_grid(n: int) -> torch.Tensor:
 
 
 # kernels launched per C-ABI call (render_bwd = prep + object kernel; paste_bwd's memset is not a kernel)
-_LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0}
+_LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0, "spair_sweep_max_rows": 0}
 LAUNCH_COUNT = 0
 
 
@@ -241,6 +256,36 @@ def pres_head_bwd(y, u, cells, B, HW, wheel, d_local, d_img, d_y):
 def relu_bwd(dh, h):
     _check(lib().spair_relu_bwd(_ptr(dh), _ld(dh), _ptr(h), _ld(h), dh.shape[0], dh.shape[1], _stream()),
            "spair_relu_bwd")
+
+
+# ----------------------------------------------------------------------------------------
+# fused forward sweep
+# ----------------------------------------------------------------------------------------
+def sweep_max_rows() -> int:
+    return lib().spair_sweep_max_rows()
+
+
+def sweep_mlp_desc(wts, biases, X, H0, H1, Y) -> SweepMLP:
+    """wts: transposed weights [K,N] (contiguous) of the two hidden layers and the output layer."""
+    m = SweepMLP()
+    for i, (w, b) in enumerate(zip(wts, biases)):
+        m.wt[i], m.b[i] = _ptr(_contig(w, "wt")), _ptr(_contig(b, "bias"))
+        m.k[i], m.n[i] = w.shape[0], w.shape[1]
+    m.x, m.ld_x, m.h0, m.h1, m.y = _ptr(_contig(X, "X")), X.shape[1], _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), \
+        _ptr(_contig(Y, "Y"))
+    return m
+
+
+def sweep_fwd(dims: SweepDims, order, starts, offsets, image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, geom,
+              mlps, box, z_where, attr, depth, pres, dmean, dstd):
+    arr, _ = _offsets_array(offsets)
+    for t in (image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, box, z_where, attr, depth, pres, dmean, dstd):
+        _contig(t, "sweep tensor")
+    _check(lib().spair_sweep_fwd(ctypes.byref(dims), _iptr(order), _iptr(starts), arr, _ptr(image), _ptr(feat), _ptr(edge),
+                                 _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), ctypes.byref(geom),
+                                 ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]), ctypes.byref(mlps[3]),
+                                 _ptr(box), _ptr(z_where), _ptr(attr), _ptr(depth), _ptr(pres), _ptr(dmean), _ptr(dstd),
+                                 _stream()), "spair_sweep_fwd")
 
 
 # ----------------------------------------------------------------------------------------

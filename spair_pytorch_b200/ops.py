@@ -169,7 +169,9 @@ class SweepPlan:
     Ih: int
     Iw: int
     G: int
+    fused_forward: bool = True         # one persistent launch for the forward sweep when the shape allows it
     order_dev: torch.Tensor = None     # int32 [HW] cells in wavefront-major order
+    starts_dev: torch.Tensor = None    # int32 [T+1]
     wf_pos_dev: torch.Tensor = None    # int32 [HW]
     missing_dev: torch.Tensor = None   # float [HW, n_nb] by position
     gather_index: torch.Tensor = None  # int64 [HW] wf_pos as gather index
@@ -187,6 +189,7 @@ class SweepPlan:
         s = self.schedule
         self.order_dev = torch.from_numpy(np.ascontiguousarray(s.order)).to(device=device, dtype=torch.int32)
         self.wf_pos_dev = torch.from_numpy(np.ascontiguousarray(s.wf_pos)).to(device=device, dtype=torch.int32)
+        self.starts_dev = torch.from_numpy(np.ascontiguousarray(s.starts)).to(device=device, dtype=torch.int32)
         self.missing_dev = torch.from_numpy(s.missing.astype(np.float32)).to(device)
         self.gather_index = self.wf_pos_dev.long()
         return self
@@ -283,7 +286,20 @@ class CellSweepFunction(torch.autograd.Function):
         dstd = torch.empty(B, HW, D, device=dev)
         c_pt, c_box, c_attr, c_depth = F + CTX, F + CTX + P, F + CTX + P + 4, F + CTX + P + 4 + A
 
-        for t in range(s.n_wavefronts):
+        mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
+        max_rows = K.sweep_max_rows() if plan.fused_forward else 0
+        fused = (max_rows >= s.max_cells and all(len(m.H) == 2 and max(m.widths) <= 256 for m in mlps) and G <= 64)
+        if fused:
+            # ONE persistent launch: a CTA owns `ipc` images and walks all wavefronts (csrc/sweep.cu)
+            ipc = max(1, min(2, max_rows // s.max_cells))
+            dims = K.SweepDims(B=B, HW=HW, Hc=s.Hc, Wc=s.Wc, F=F, A=A, P=P, C=plan.C, Ih=plan.Ih, Iw=plan.Iw, G=G, ipc=ipc,
+                               n_wavefronts=s.n_wavefronts, max_cells=s.max_cells, n_nb=len(s.offsets))
+            wts = [[w.t().contiguous() for w in m.W] for m in mlps]     # kept alive until the launch is enqueued
+            descs = [K.sweep_mlp_desc(wt, m.b, m.X, m.H[0], m.H[1], m.Y) for wt, m in zip(wts, mlps)]
+            K.sweep_fwd(dims, plan.order_dev, plan.starts_dev, s.offsets, x, feat, edge, eps_where, eps_attr, eps_depth,
+                        u_pres, plan.geom, descs, box, z_where, attr, depth, pres, dmean, dstd)
+
+        for t in range(s.n_wavefronts if not fused else 0):
             c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
             r0, r1 = c0 * B, c1 * B
             cells = plan.order_dev[c0:c1]
@@ -303,6 +319,7 @@ class CellSweepFunction(torch.autograd.Function):
             K.pres_head_fwd(obj_mlp.Y[r0:r1], u_pres, cells, B, HW, pres)
 
         ctx.plan = plan
+        plan.last_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)      # inspection hook for tests (no copy)
         ctx.mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
         ctx.noise = (eps_where, eps_attr, eps_depth, u_pres, wheel)
         ctx.x = x

@@ -25,6 +25,10 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "require_cuda", lambda *a, **k: None)
 
 
+def sweep_max_rows():
+    return 0        # the fused forward sweep has no test double: host-logic tests exercise the per-wavefront path
+
+
 def _rows(cells, B):
     return [int(c) for c in cells.tolist()]
 

@@ -89,6 +89,9 @@ def model_cases():
                 fx["dist_std/" + n] = d.scale.detach().numpy()
                 assert torch.equal(d.loc, out["dist_mean"][n])
             fx.update(param_checksums(net.state_dict()))
+            # float64 evaluation of the same formulas: tells rounding noise of the reference's own fp32 backward
+            # (and ReLU/clamp kink decisions) apart from genuine differences
+            _, params64 = so.forward_backward_fp64(net.state_dict(), x, step, noise, ocfg)
             for k, p in net.named_parameters():
                 if p.grad is None:
                     fx["gnone/" + k] = np.array(1)
@@ -97,6 +100,7 @@ def model_cases():
                 idx = grad_sample_indices(k, g.numel())
                 fx["gidx/" + k] = idx.astype(np.int64)
                 fx["gval/" + k] = g[torch.from_numpy(idx)].numpy()
+                fx["g64val/" + k] = params64[k].grad.detach().flatten()[torch.from_numpy(idx)].numpy()
                 fx["gstat/" + k] = np.array([g.double().sum().item(), g.double().norm().item()])
             path = os.path.join(HERE, "model_%s_step%d.npz" % (name, step))
             np.savez_compressed(path, **fx)

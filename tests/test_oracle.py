@@ -190,4 +190,4 @@ def test_base_grid_matches_torch_affine_grid_bit_exactly():
 def test_invalid_arguments_rejected_without_gpu():
     from spair_pytorch_b200 import kernels as K
     assert K.lib().spair_base_grid(0, None) == -1
-    assert K.lib().spair_render_num_tiles(2, 128, 128) == 2 * 8 * 4
+    assert K.lib().spair_render_num_tiles(2, 128, 128) == 2 * 4 * 4      # 32x32 canvas tiles
