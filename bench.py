@@ -222,6 +222,7 @@ def run_ours(args):
     rank, world, local_rank = dp.init_distributed("nccl" if "RANK" in os.environ else None)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.benchmark = True      # fixed shapes: let cuDNN pick its fastest fp32 algorithms for the backbone
     net = helpers.build_model(CONFIG_NAME, dev)
     ddp = dp.DataParallelSPAIR(net, world_size=world)
     ddp.broadcast_parameters()

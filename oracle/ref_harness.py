@@ -98,7 +98,8 @@ def load_reference(overrides: dict | None = None) -> types.SimpleNamespace:
         debug_tools.plot_prerender_components = lambda *a, **k: None
         modules = importlib.import_module("spair.modules")
         models = importlib.import_module("spair.models")
-        ns = types.SimpleNamespace(cfg=cfg, modules=modules, models=models, debug_tools=debug_tools)
+        metric = importlib.import_module("spair.metric")
+        ns = types.SimpleNamespace(cfg=cfg, modules=modules, models=models, debug_tools=debug_tools, metric=metric)
     finally:
         sys.path.remove(REFERENCE_ROOT)
         for k in [k for k in sys.modules if k == "spair" or k.startswith("spair.")]:

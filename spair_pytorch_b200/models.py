@@ -65,9 +65,9 @@ class SPAIR(nn.Module):
         if "SPAIR_ALLOW_TF32" not in os.environ:   # fp32 parity with the reference's CPU path
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
-        if "SPAIR_NONDETERMINISTIC_CUDNN" not in os.environ:
-            # the hand-written kernels are bitwise reproducible; keep the cuDNN convs that way too
-            # (its default backward-filter algorithm for the 1-channel first conv uses atomics)
+        if "SPAIR_DETERMINISTIC" in os.environ:
+            # the hand-written kernels are bitwise reproducible; this makes the cuDNN backbone reproducible too (its
+            # default backward-filter algorithms use atomics) at the price of ~2x slower convolutions
             torch.backends.cudnn.deterministic = True
         print('model initialized')
 

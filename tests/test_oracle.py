@@ -191,3 +191,20 @@ def test_invalid_arguments_rejected_without_gpu():
     from spair_pytorch_b200 import kernels as K
     assert K.lib().spair_base_grid(0, None) == -1
     assert K.lib().spair_render_num_tiles(2, 128, 128) == 2 * 4 * 4      # 32x32 canvas tiles
+
+
+def test_device_scene_generator_schema():
+    """Procedural scenes: values in [0,1], boxes inside the canvas, counts in 1..max — same item schema
+    as the reference's HDF5 dataset (dataloader.py:23-33)."""
+    from spair_pytorch_b200.dataloader import scattered_sprites, scattered_sprites_gpu
+    g = torch.Generator().manual_seed(0)
+    for shape in ((1, 128, 128), (3, 64, 64)):
+        img, bbox, count = scattered_sprites_gpu(6, shape, "cpu", g, max_sprites=9, sprite_px=(8, 20))
+        assert img.shape == (6,) + shape and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+        assert bbox.shape == (6, 9, 4) and count.shape == (6, 1) and 1 <= float(count.min()) and float(count.max()) <= 9
+        live = bbox[..., 2] > 0
+        assert bool(((bbox[..., 0] + bbox[..., 2])[live] <= shape[2]).all()) and bool(((bbox[..., 1] + bbox[..., 3])[live] <= shape[1]).all())
+        assert int(live.sum()) == int(count.sum())
+        assert float(img.flatten(1).max(1).values.min()) > 0.5        # every image has at least one visible sprite
+    img2, box2, cnt2 = scattered_sprites(3, (1, 128, 128), seed=1, return_boxes=True)
+    assert img2.shape == (3, 1, 128, 128) and box2.shape == (3, 9, 4) and cnt2.shape == (3, 1)

@@ -55,3 +55,28 @@ def test_seeded_construction_reproduces_reference_parameters():
     assert list(rs) == list(os_)
     for k in rs:
         assert torch.equal(rs[k], os_[k]), k
+
+
+def test_metrics_match_reference():
+    """spair.metric (evaluation path, reference metric.py:5-100) on random boxes."""
+    from spair_pytorch_b200 import config as cfg
+    from spair_pytorch_b200 import metric as ours
+    ns = rh.load_reference(dict(BATCH_SIZE=4))
+    g = torch.Generator().manual_seed(1)
+    saved = cfg.BATCH_SIZE
+    cfg.BATCH_SIZE = 4
+    try:
+        z_where = torch.rand(4, 4, 11, 11, generator=g) * 0.4
+        z_pres = torch.rand(4, 1, 11, 11, generator=g)
+        gt = torch.rand(4, 9, 4, generator=g) * 40 + 5
+        count = torch.randint(1, 10, (4, 1), generator=g).float()
+        a = ns.metric.mAP(z_where.clone(), z_pres.clone(), gt.clone(), count.clone())
+        b = ours.mAP(z_where.clone(), z_pres.clone(), gt.clone(), count.clone())
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+        assert torch.equal(ns.metric.object_count_accuracy(z_pres, count), ours.object_count_accuracy(z_pres, count))
+        box_a, box_b = torch.rand(4, 7, 4, generator=g), torch.rand(4, 5, 4, generator=g)
+        box_a[..., 2:] += box_a[..., :2]
+        box_b[..., 2:] += box_b[..., :2]
+        assert torch.allclose(ns.metric.batch_jaccard(box_a, box_b), ours.batch_jaccard(box_a, box_b), rtol=1e-6, atol=1e-7)
+    finally:
+        cfg.BATCH_SIZE = saved

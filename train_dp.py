@@ -75,6 +75,7 @@ def main():
         except ImportError:
             pass
 
+    torch.backends.cudnn.benchmark = True                         # fixed shapes: fastest fp32 conv algorithms
     torch.manual_seed(3)                                          # train.py:39
     net = SPAIR(cfg.INPUT_IMAGE_SHAPE, writer if args.eager else _NullWriter(), dev).to(dev)
     ddp = dp.DataParallelSPAIR(net, world_size=world)
