@@ -60,7 +60,8 @@ class GradientBucket:
         off = 0
         for _, p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            # same strides as the parameter (e.g. channels_last conv weights): fused optimisers require matching layouts
+            p.grad = self.flat[off:off + n].as_strided(p.shape, p.stride())
             off += n
 
     @property
