@@ -285,6 +285,33 @@ int spair_sweep_fwd(const spair_sweep_dims* dims,        /* host */
                     float* dmean, float* dstd,           /* image-major outputs */
                     void* stream);
 
+/* Backward of the fused sweep, same image partition, wavefronts in reverse order.  Reads the forward
+ * activations (h0, h1, y of each MLP) and the UNtransposed weights w[n][k], writes dy / dh1 / dh0 / dx of every
+ * row (wavefront-major; they feed the weight-gradient GEMMs and the feature / edge-element reductions done by
+ * the caller).  d_* are the image-major gradients arriving from the renderer, the decoder and the KL terms
+ * (any may be NULL).  Replaces spair_context_grad_gather, spair_pres_head_bwd, spair_normal_head_bwd x2,
+ * spair_glimpse_bwd, spair_box_head_bwd, spair_relu_bwd and the per-wavefront dX GEMMs. */
+typedef struct spair_sweep_mlp_bwd {
+    const float* w[3];      /* weights as stored, [n][k], of hidden0, hidden1, output */
+    int k[3], n[3];
+    const float* h0; const float* h1; const float* y;   /* forward activations */
+    float* dx; int ld_dx;   /* [HW*B, ld_dx] gradient wrt the input rows (written) */
+    float* dh0; float* dh1; float* dy;                  /* written */
+} spair_sweep_mlp_bwd;
+
+int spair_sweep_bwd(const spair_sweep_dims* dims, const int* order, const int* starts,
+                    const int* wf_pos,                   /* [HW] position of each cell in wavefront-major order (device) */
+                    const int* nb_offsets,               /* host */
+                    const float* image, const float* z_where,
+                    const float* eps_where, const float* eps_attr, const float* eps_depth, const float* u_pres,
+                    const float* wheel,                  /* device scalar */
+                    const spair_box_geom* geom,
+                    const spair_sweep_mlp_bwd* box_mlp, const spair_sweep_mlp_bwd* enc_mlp,
+                    const spair_sweep_mlp_bwd* z_mlp, const spair_sweep_mlp_bwd* obj_mlp,
+                    const float* d_zw, const float* d_attr, const float* d_depth, const float* d_pres,
+                    const float* d_dmean, const float* d_dstd,
+                    void* stream);
+
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
 

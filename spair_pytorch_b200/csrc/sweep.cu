@@ -327,6 +327,293 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
     }
 }
 
+
+// =================================================================================================================
+// Fused backward sweep: the hand-written backward of the cell loop (ops.CellSweepFunction.backward) in one launch.
+// Same image partition as the forward: a CTA walks the wavefronts of its images in REVERSE order.  The gradient that
+// arrives through the lateral context comes from cells of later wavefronts of the SAME image, i.e. from rows this
+// CTA has already written.  Per wavefront: context-gradient gather -> presence head -> obj MLP (dX chain) -> depth
+// head -> z MLP -> attr head -> encoder MLP -> glimpse (d z_where) -> box head -> box MLP.  A backward layer
+// dX = dY . W is the same register-tiled dot product as the forward with the UNtransposed weight W[n][k] (reduction
+// over n, coalesced over k) and a ReLU-mask epilogue.  dY / dH / dX of every row are written to the wavefront-major
+// global buffers: the 13 weight gradients stay one large cuBLAS GEMM each over all rows, after the sweep.
+// =================================================================================================================
+struct SweepMLPBwd {
+    const float* W[3];     // [N][K] weights as stored (hidden0, hidden1, output)
+    int K[3], N[3];
+    const float* H0; const float* H1; const float* Y;   // forward activations
+    float* dX; int ldX; float* dH0; float* dH1; float* dY;
+};
+
+struct SweepBwdArgs {
+    int B, HW, Hc, Wc, F, A, P, C, Ih, Iw, G, ipc, n_wavefronts;
+    NeighbourList nb;
+    const int* order; const int* starts; const int* wf_pos;
+    const float* image; const float* z_where;
+    const float* eps_where; const float* eps_attr; const float* eps_depth; const float* u_pres;
+    const float* wheel;
+    spair_box_geom geom;
+    SweepMLPBwd box, enc, z, obj;
+    const float* encX; int ld_encX;      // unused (glimpse is re-sampled), kept for symmetry
+    const float* d_zw; const float* d_attr; const float* d_depth; const float* d_pres;   // image-major upstream (may be null)
+    const float* d_dmean; const float* d_dstd;
+};
+
+// out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), columns processed in passes of 128
+__device__ void dense_bwd_layer(const float* __restrict__ W, int Nred, int Kout, const float* g_smem,
+                                const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows,
+                                float* out_smem, float* __restrict__ out_glob, int ld_out) {
+    constexpr int RG = 4, NCOLP = kSwThreads * RG / kSwRows;
+    const int row0 = (threadIdx.x / NCOLP) * RG;
+    const int kc = (Nred + 3) & ~3;
+    if (out_smem)
+        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + Kout + (idx & 3)] = 0.0f;
+    for (int c0 = 0; c0 < Kout; c0 += NCOLP) {
+        const int col = c0 + threadIdx.x % NCOLP;
+        if (col < Kout && row0 < nrows) {
+            float acc[RG];
+#pragma unroll
+            for (int r = 0; r < RG; ++r) acc[r] = 0.0f;
+            dense_accumulate<RG>(acc, W, Kout, col, 0, kc, Nred, g_smem, kSwHP, row0);
+#pragma unroll
+            for (int r = 0; r < RG; ++r) {
+                const int row = row0 + r;
+                float v = acc[r];
+                if (row < nrows) {
+                    const size_t g = grow[row];
+                    if (Hmask && !(Hmask[g * Kout + col] > 0.0f)) v = 0.0f;
+                    out_glob[g * ld_out + col] = v;
+                } else {
+                    v = 0.0f;
+                }
+                if (out_smem) out_smem[row * kSwHP + col] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// dY (already in shared memory `gy` and in global M.dY) -> dH1 -> dH0 -> dX
+__device__ __forceinline__ void mlp3_bwd(const SweepMLPBwd& M, const int* grow, int nrows, float* gy, float* ga, float* gb) {
+    dense_bwd_layer(M.W[2], M.N[2], M.K[2], gy, M.H1, grow, nrows, ga, M.dH1, M.K[2]);
+    dense_bwd_layer(M.W[1], M.N[1], M.K[1], ga, M.H0, grow, nrows, gb, M.dH0, M.K[1]);
+    dense_bwd_layer(M.W[0], M.N[0], M.K[0], gb, nullptr, grow, nrows, nullptr, M.dX, M.ldX);
+}
+
+__global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p) {
+    static_assert(kSwThreads / 32 == kSwRows, "the glimpse gradient uses one warp per row");
+    extern __shared__ __align__(16) float sm[];
+    float* gy = sm;                                     // [kSwRows][kSwHP] dY of the current network
+    float* ga = gy + kSwRows * kSwHP;
+    float* gb = ga + kSwRows * kSwHP;
+    float* dcell = gb + kSwRows * kSwHP;                // [kSwRows][64] gradient through the lateral context
+    float* base_g = dcell + kSwRows * 64;               // [kSwMaxG]
+    float* dzw = base_g + kSwMaxG;                      // [kSwRows][4] glimpse gradient wrt z_where
+    int* grow = reinterpret_cast<int*>(dzw + kSwRows * 4);
+    int* rcell = grow + kSwRows;
+    int* rimg = rcell + kSwRows;
+
+    const int b0 = blockIdx.x * p.ipc;
+    const int n_img = min(p.ipc, p.B - b0);
+    if (n_img <= 0) return;
+    const int E = p.A + 6, D = 4 + p.A + 1;
+    const int CTX = p.nb.n * E;
+    const int c_pt = p.F + CTX, c_box = c_pt + p.P, c_attr = c_box + 4, c_depth = c_attr + p.A;
+    const int GG = p.G * p.G;
+    const float keep = 1.0f - p.wheel[0];
+    for (int j = threadIdx.x; j < p.G; j += kSwThreads) base_g[j] = base_coord(j, p.G);
+
+    for (int t = p.n_wavefronts - 1; t >= 0; --t) {
+        const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
+        const int nrows = n_cells * n_img;
+        __syncthreads();
+        if (threadIdx.x < kSwRows) {
+            const int r = threadIdx.x;
+            if (r < nrows) {
+                const int k = r / n_img, li = r - k * n_img;
+                grow[r] = (s0 + k) * p.B + b0 + li;
+                rcell[r] = p.order[s0 + k];
+                rimg[r] = b0 + li;
+            } else {
+                grow[r] = 0; rcell[r] = 0; rimg[r] = b0;
+            }
+        }
+        __syncthreads();
+
+        // ---- gradient arriving through the lateral context of later cells (models.py:106 -> 73) ----
+        for (int idx = threadIdx.x; idx < nrows * E; idx += kSwThreads) {
+            const int r = idx / E, j = idx - r * E;
+            const int b = rimg[r], cell = rcell[r];
+            const int h = cell / p.Wc, w = cell - h * p.Wc;
+            float acc = 0.0f;
+            for (int s = 0; s < p.nb.n; ++s) {
+                const int ch = h - p.nb.dh[s], cw = w - p.nb.dw[s];
+                if (ch < 0 || ch >= p.Hc || cw < 0 || cw >= p.Wc) continue;
+                const size_t cr = (size_t)p.wf_pos[ch * p.Wc + cw] * p.B + b;      // row written by this CTA earlier
+                const int c = p.F + s * E + j;
+                acc += p.box.dX[cr * p.box.ldX + c] + p.z.dX[cr * p.z.ldX + c] + p.obj.dX[cr * p.obj.ldX + c];
+            }
+            dcell[r * 64 + j] = acc;
+        }
+        __syncthreads();
+
+        // ---- z_pres (models.py:393-411) ----
+        if (threadIdx.x < kSwRows) {
+            const int r = threadIdx.x;
+            float dy = 0.0f;
+            if (r < nrows) {
+                const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+                const float logit = p.obj.Y[grow[r]];
+                const float u = __ldg(p.u_pres + o);
+                const float pr = sigmoid_f(clamp10(logit) + (logf(u + 10e-10f) - logf(1.0f - u + 10e-10f)));
+                const float d = dcell[r * 64 + E - 1] + (p.d_pres ? __ldg(p.d_pres + o) : 0.0f);
+                dy = keep * d * pr * (1.0f - pr) * clamp10_mask(logit);
+                p.obj.dY[grow[r]] = dy;
+            }
+            gy[r * kSwHP + 0] = dy;
+            gy[r * kSwHP + 1] = gy[r * kSwHP + 2] = gy[r * kSwHP + 3] = 0.0f;
+        }
+        __syncthreads();
+        mlp3_bwd(p.obj, grow, nrows, gy, ga, gb);
+
+        // ---- z_depth (models.py:88-97) ----
+        for (int idx = threadIdx.x; idx < kSwRows * (2 + p.P); idx += kSwThreads) {
+            const int r = idx / (2 + p.P), k = idx - r * (2 + p.P);
+            float v = 0.0f;
+            if (r < nrows) {
+                const size_t g = grow[r];
+                if (k >= 2) {
+                    v = p.obj.dX[g * p.obj.ldX + c_pt + (k - 2)];               // passthrough features fed the obj network
+                } else {
+                    const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+                    const float* yr = p.z.Y + g * p.z.N[2];
+                    const float ls = yr[1], sg = sigmoid_f(clamp10(ls)), e = __ldg(p.eps_depth + o);
+                    const float zl = yr[0] + e * (sg * 2.0f);
+                    const float sq = sigmoid_f(clamp10(zl));
+                    const float d_o = p.obj.dX[g * p.obj.ldX + c_depth] + dcell[r * 64 + E - 2] + (p.d_depth ? __ldg(p.d_depth + o) : 0.0f);
+                    const float d_z = d_o * 4.0f * sq * (1.0f - sq) * clamp10_mask(zl);
+                    if (k == 0) v = keep * (d_z + (p.d_dmean ? __ldg(p.d_dmean + o * D + D - 1) : 0.0f));
+                    else v = keep * ((d_z * e + (p.d_dstd ? __ldg(p.d_dstd + o * D + D - 1) : 0.0f)) * 2.0f * sg * (1.0f - sg) * clamp10_mask(ls));
+                }
+                p.z.dY[g * p.z.N[2] + k] = v;
+            }
+            gy[r * kSwHP + k] = v;
+        }
+        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 + p.P + (idx & 3)] = 0.0f;
+        __syncthreads();
+        mlp3_bwd(p.z, grow, nrows, gy, ga, gb);
+
+        // ---- z_what (models.py:83-85) ----
+        for (int idx = threadIdx.x; idx < kSwRows * p.A; idx += kSwThreads) {
+            const int r = idx / p.A, k = idx - r * p.A;
+            float vm = 0.0f, vs = 0.0f;
+            if (r < nrows) {
+                const size_t g = grow[r];
+                const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+                const float* yr = p.enc.Y + g * p.enc.N[2];
+                const float ls = yr[p.A + k], sg = sigmoid_f(clamp10(ls)), e = __ldg(p.eps_attr + o * p.A + k);
+                const float d_o = p.z.dX[g * p.z.ldX + c_attr + k] + p.obj.dX[g * p.obj.ldX + c_attr + k] + dcell[r * 64 + 4 + k] +
+                                  (p.d_attr ? __ldg(p.d_attr + o * p.A + k) : 0.0f);
+                vm = d_o + (p.d_dmean ? __ldg(p.d_dmean + o * D + 4 + k) : 0.0f);
+                vs = (d_o * e + (p.d_dstd ? __ldg(p.d_dstd + o * D + 4 + k) : 0.0f)) * 2.0f * sg * (1.0f - sg) * clamp10_mask(ls);
+                p.enc.dY[g * p.enc.N[2] + k] = vm;
+                p.enc.dY[g * p.enc.N[2] + p.A + k] = vs;
+            }
+            gy[r * kSwHP + k] = vm;
+            gy[r * kSwHP + p.A + k] = vs;
+        }
+        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 * p.A + (idx & 3)] = 0.0f;
+        __syncthreads();
+        mlp3_bwd(p.enc, grow, nrows, gy, ga, gb);
+
+        // ---- glimpse: d z_where (modules.py:216-273; the image has no gradient in the model) ----
+        // one warp per row (kSwThreads / 32 == kSwRows): lanes stride over the texels, one butterfly reduction per row —
+        // deterministic, no atomics
+        {
+            const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            if (r < nrows) {
+                const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+                const float4 zw = *reinterpret_cast<const float4*>(p.z_where + o * 4);
+                const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
+                const float* grow_e = p.enc.dX + (size_t)grow[r] * p.enc.ldX;
+                for (int tt = lane; tt < GG; tt += 32) {
+                    const int i = tt / p.G, j = tt - i * p.G;
+                    float ix = unnormalize(affine_coord(base_g[j], A.ax, A.cx), 0.5f * (float)p.Iw);
+                    float iy = unnormalize(affine_coord(base_g[i], A.ay, A.cy), 0.5f * (float)p.Ih);
+                    const float mx = (ix > 0.0f && ix < (float)(p.Iw - 1)) ? 1.0f : 0.0f;
+                    const float my = (iy > 0.0f && iy < (float)(p.Ih - 1)) ? 1.0f : 0.0f;
+                    ix = fminf(fmaxf(ix, 0.0f), (float)(p.Iw - 1));
+                    iy = fminf(fmaxf(iy, 0.0f), (float)(p.Ih - 1));
+                    const float fx0 = floorf(ix), fy0 = floorf(iy);
+                    const int x0 = (int)fx0, y0 = (int)fy0;
+                    const int x1 = min(x0 + 1, p.Iw - 1), y1 = min(y0 + 1, p.Ih - 1);
+                    const float wx1 = ix - fx0, wx0 = fx0 + 1.0f - ix, wy1 = iy - fy0, wy0 = fy0 + 1.0f - iy;
+                    float gix = 0.0f, giy = 0.0f;
+                    for (int c = 0; c < p.C; ++c) {
+                        const float* pl = p.image + ((size_t)rimg[r] * p.C + c) * p.Ih * p.Iw;
+                        const float v00 = __ldg(pl + (size_t)y0 * p.Iw + x0), v01 = __ldg(pl + (size_t)y0 * p.Iw + x1);
+                        const float v10 = __ldg(pl + (size_t)y1 * p.Iw + x0), v11 = __ldg(pl + (size_t)y1 * p.Iw + x1);
+                        const float g = grow_e[c * GG + tt];
+                        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+                        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+                    }
+                    const float dgx = gix * mx, dgy = giy * my;
+                    a0 += dgx;
+                    a1 += dgy;
+                    a2 = fmaf(dgx, base_g[j], a2);
+                    a3 = fmaf(dgy, base_g[i], a3);
+                }
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+            if (lane == 0) { dzw[r * 4 + 0] = a0; dzw[r * 4 + 1] = a1; dzw[r * 4 + 2] = a2; dzw[r * 4 + 3] = a3; }
+        }
+        __syncthreads();
+
+        // ---- z_where: box head (models.py:322-381) ----
+        for (int idx = threadIdx.x; idx < kSwRows * (8 + p.P); idx += kSwThreads) {
+            const int r = idx / (8 + p.P), k = idx - r * (8 + p.P);
+            float v = 0.0f;
+            if (r < nrows) {
+                const size_t g = grow[r];
+                if (k >= 8) {
+                    v = p.z.dX[g * p.z.ldX + c_pt + (k - 8)];                    // passthrough features fed the z network
+                } else {
+                    const int kk = k & 3;                                        // component: cy, cx, height, width
+                    const int slot = sw_box_slot(kk);
+                    const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
+                    const float* yr = p.box.Y + g * p.box.N[2];
+                    const float ls = yr[4 + kk], sg = sigmoid_f(clamp10(ls)), e = __ldg(p.eps_where + o * 4 + kk);
+                    const float zl = yr[kk] + e * (sg * 2.0f);
+                    const float sq = sigmoid_f(clamp10(zl));
+                    float d_b = p.z.dX[g * p.z.ldX + c_box + slot] + p.obj.dX[g * p.obj.ldX + c_box + slot] + dcell[r * 64 + slot];
+                    // glimpse gradient (d gx sums) -> d z_where: gx = xs*base + (2xt-1), ix = (gx+1)*I/2 - 0.5
+                    const float hI = 0.5f * ((slot == 0 || slot == 2) ? (float)p.Iw : (float)p.Ih);
+                    const float d_zw_glimpse = (slot == 0) ? 2.0f * hI * dzw[r * 4 + 0] : (slot == 1) ? 2.0f * hI * dzw[r * 4 + 1]
+                                             : (slot == 2) ? hI * dzw[r * 4 + 2] : hI * dzw[r * 4 + 3];
+                    const float d_zwv = d_zw_glimpse + (p.d_zw ? __ldg(p.d_zw + o * 4 + slot) : 0.0f);
+                    float d_s;
+                    if (kk < 2) {
+                        d_b += d_zwv * (kk == 0 ? p.geom.cell_ratio_y : p.geom.cell_ratio_x);
+                        d_s = d_b * p.geom.yx_scale;
+                    } else {
+                        d_b += (d_zwv / (kk == 2 ? p.geom.img_h : p.geom.img_w)) * p.geom.anchor;
+                        d_s = d_b * p.geom.hw_scale;
+                    }
+                    const float d_zl = d_s * sq * (1.0f - sq) * clamp10_mask(zl);
+                    if (k < 4) v = keep * (d_zl + (p.d_dmean ? __ldg(p.d_dmean + o * D + kk) : 0.0f));
+                    else v = keep * ((d_zl * e + (p.d_dstd ? __ldg(p.d_dstd + o * D + kk) : 0.0f)) * 2.0f * sg * (1.0f - sg) * clamp10_mask(ls));
+                }
+                p.box.dY[g * p.box.N[2] + k] = v;
+            }
+            gy[r * kSwHP + k] = v;
+        }
+        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 8 + p.P + (idx & 3)] = 0.0f;
+        __syncthreads();
+        mlp3_bwd(p.box, grow, nrows, gy, ga, gb);
+    }
+}
+
 }  // namespace spair
 
 using namespace spair;
@@ -378,5 +665,54 @@ extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, cons
     }
     const int grid = (d->B + d->ipc - 1) / d->ipc;
     sweep_fwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
+    SPAIR_LAUNCH_CHECK();
+}
+
+static bool to_mlp_bwd(const spair_sweep_mlp_bwd* m, SweepMLPBwd& out) {
+    if (!m || !m->h0 || !m->h1 || !m->y || !m->dx || !m->dh0 || !m->dh1 || !m->dy) return false;
+    for (int i = 0; i < 3; ++i) {
+        if (!m->w[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
+        out.W[i] = m->w[i]; out.K[i] = m->k[i]; out.N[i] = m->n[i];
+    }
+    if (m->k[1] != m->n[0] || m->k[2] != m->n[1] || m->ld_dx < m->k[0]) return false;
+    out.H0 = m->h0; out.H1 = m->h1; out.Y = m->y; out.dX = m->dx; out.ldX = m->ld_dx;
+    out.dH0 = m->dh0; out.dH1 = m->dh1; out.dY = m->dy;
+    return true;
+}
+
+extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* wf_pos,
+                               const int* nb_offsets, const float* image, const float* z_where, const float* eps_where,
+                               const float* eps_attr, const float* eps_depth, const float* u_pres, const float* wheel,
+                               const spair_box_geom* geom, const spair_sweep_mlp_bwd* box_mlp,
+                               const spair_sweep_mlp_bwd* enc_mlp, const spair_sweep_mlp_bwd* z_mlp,
+                               const spair_sweep_mlp_bwd* obj_mlp, const float* d_zw, const float* d_attr,
+                               const float* d_depth, const float* d_pres, const float* d_dmean, const float* d_dstd,
+                               void* stream) {
+    SPAIR_REQUIRE(d && order && starts && wf_pos && nb_offsets && image && z_where && eps_where && eps_attr && eps_depth && u_pres);
+    SPAIR_REQUIRE(wheel && geom && ((uintptr_t)z_where % 16) == 0 && (d_dmean == nullptr) == (d_dstd == nullptr));
+    SPAIR_REQUIRE(d->B > 0 && d->HW == d->Hc * d->Wc && d->G > 0 && d->G <= kSwMaxG && d->ipc >= 1 && d->n_wavefronts > 0);
+    SPAIR_REQUIRE(d->max_cells * d->ipc <= kSwRows && d->n_nb >= 1 && d->n_nb <= SPAIR_MAX_NEIGHBOURS && d->A + 6 <= 64);
+    SweepBwdArgs a;
+    a.B = d->B; a.HW = d->HW; a.Hc = d->Hc; a.Wc = d->Wc; a.F = d->F; a.A = d->A; a.P = d->P; a.C = d->C;
+    a.Ih = d->Ih; a.Iw = d->Iw; a.G = d->G; a.ipc = d->ipc; a.n_wavefronts = d->n_wavefronts;
+    a.nb.n = d->n_nb;
+    for (int i = 0; i < d->n_nb; ++i) { a.nb.dh[i] = nb_offsets[2 * i]; a.nb.dw[i] = nb_offsets[2 * i + 1]; }
+    a.order = order; a.starts = starts; a.wf_pos = wf_pos; a.image = image; a.z_where = z_where;
+    a.eps_where = eps_where; a.eps_attr = eps_attr; a.eps_depth = eps_depth; a.u_pres = u_pres; a.wheel = wheel;
+    a.geom = *geom;
+    SPAIR_REQUIRE(to_mlp_bwd(box_mlp, a.box) && to_mlp_bwd(enc_mlp, a.enc) && to_mlp_bwd(z_mlp, a.z) && to_mlp_bwd(obj_mlp, a.obj));
+    const int E = d->A + 6, CTX = d->n_nb * E;
+    SPAIR_REQUIRE(a.box.K[0] == d->F + CTX && a.box.N[2] == 8 + d->P && a.enc.K[0] == d->C * d->G * d->G && a.enc.N[2] == 2 * d->A);
+    SPAIR_REQUIRE(a.z.K[0] == d->F + CTX + d->P + 4 + d->A && a.z.N[2] == 2 + d->P && a.obj.K[0] == a.z.K[0] + 1 && a.obj.N[2] == 1);
+    a.encX = nullptr; a.ld_encX = 0;
+    a.d_zw = d_zw; a.d_attr = d_attr; a.d_depth = d_depth; a.d_pres = d_pres; a.d_dmean = d_dmean; a.d_dstd = d_dstd;
+    const size_t smem = sizeof(float) * (size_t)(3 * kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) + sizeof(int) * 3 * kSwRows;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sweep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int grid = (d->B + d->ipc - 1) / d->ipc;
+    sweep_bwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
     SPAIR_LAUNCH_CHECK();
 }

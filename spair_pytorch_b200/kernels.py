@@ -40,6 +40,14 @@ class SweepMLP(ctypes.Structure):
                 ("y", ctypes.c_void_p)]
 
 
+class SweepMLPBwd(ctypes.Structure):
+    """``spair_sweep_mlp_bwd`` of include/spair_b200.h."""
+    _fields_ = [("w", ctypes.c_void_p * 3), ("k", ctypes.c_int * 3), ("n", ctypes.c_int * 3),
+                ("h0", ctypes.c_void_p), ("h1", ctypes.c_void_p), ("y", ctypes.c_void_p),
+                ("dx", ctypes.c_void_p), ("ld_dx", ctypes.c_int), ("dh0", ctypes.c_void_p), ("dh1", ctypes.c_void_p),
+                ("dy", ctypes.c_void_p)]
+
+
 class SpairKernelError(RuntimeError):
     pass
 
@@ -70,6 +78,7 @@ _SIGNATURES = {
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_fwd": [_P] * 23 + [_P],
+    "spair_sweep_bwd": [_P] * 23 + [_P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -286,6 +295,30 @@ def sweep_fwd(dims: SweepDims, order, starts, offsets, image, feat, edge, eps_wh
                                  ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]), ctypes.byref(mlps[3]),
                                  _ptr(box), _ptr(z_where), _ptr(attr), _ptr(depth), _ptr(pres), _ptr(dmean), _ptr(dstd),
                                  _stream()), "spair_sweep_fwd")
+
+
+def sweep_mlp_bwd_desc(ws, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBwd:
+    """ws: weights as stored [N,K] (contiguous) of the two hidden layers and the output layer."""
+    m = SweepMLPBwd()
+    for i, w in enumerate(ws):
+        m.w[i] = _ptr(_contig(w, "weight"))
+        m.n[i], m.k[i] = w.shape[0], w.shape[1]
+    m.h0, m.h1, m.y = _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), _ptr(_contig(Y, "Y"))
+    m.dx, m.ld_dx = _ptr(_contig(dX, "dX")), dX.shape[1]
+    m.dh0, m.dh1, m.dy = _ptr(_contig(dH0, "dH0")), _ptr(_contig(dH1, "dH1")), _ptr(_contig(dY, "dY"))
+    return m
+
+
+def sweep_bwd(dims: SweepDims, order, starts, wf_pos, offsets, image, z_where, eps_where, eps_attr, eps_depth, u_pres, wheel,
+              geom, mlps, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd):
+    arr, _ = _offsets_array(offsets)
+    for t in (image, z_where, eps_where, eps_attr, eps_depth, u_pres, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd):
+        _contig(t, "sweep tensor")
+    _check(lib().spair_sweep_bwd(ctypes.byref(dims), _iptr(order), _iptr(starts), _iptr(wf_pos), arr, _ptr(image),
+                                 _ptr(z_where), _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), _ptr(wheel),
+                                 ctypes.byref(geom), ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]),
+                                 ctypes.byref(mlps[3]), _ptr(d_zw), _ptr(d_attr), _ptr(d_depth), _ptr(d_pres), _ptr(d_dmean),
+                                 _ptr(d_dstd), _stream()), "spair_sweep_bwd")
 
 
 # ----------------------------------------------------------------------------------------

@@ -139,7 +139,7 @@ class SPAIR(nn.Module):
         plan = ops.SweepPlan(schedule=build_schedule(Hc, Wc, c.n_lookback), geom=geom, B_hint=0,
                              F=int(self.feature_space_dim[0]), A=c.n_attr, P=c.n_pass, C=C, Ih=Ih, Iw=Iw,
                              G=int(c.object_shape[0]))
-        plan.fused_forward = "SPAIR_UNFUSED_SWEEP" not in os.environ
+        plan.fused_forward = plan.fused_backward = "SPAIR_UNFUSED_SWEEP" not in os.environ
         plan.n_hidden = dict(box=len(self.box_network.body) // 2, enc=(len(self.object_encoder) - 1) // 2,
                              z=len(self.z_network.body) // 2, obj=(len(self.obj_network) - 1) // 2)
         plan.to(device)

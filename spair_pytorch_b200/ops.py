@@ -170,6 +170,7 @@ class SweepPlan:
     Iw: int
     G: int
     fused_forward: bool = True         # one persistent launch for the forward sweep when the shape allows it
+    fused_backward: bool = True        # same for the reverse sweep (needs the fused forward's bookkeeping)
     order_dev: torch.Tensor = None     # int32 [HW] cells in wavefront-major order
     starts_dev: torch.Tensor = None    # int32 [T+1]
     wf_pos_dev: torch.Tensor = None    # int32 [HW]
@@ -318,6 +319,7 @@ class CellSweepFunction(torch.autograd.Function):
             obj_mlp.forward(r0, r1)
             K.pres_head_fwd(obj_mlp.Y[r0:r1], u_pres, cells, B, HW, pres)
 
+        ctx.fused_dims = dims if fused else None
         ctx.plan = plan
         plan.last_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)      # inspection hook for tests (no copy)
         ctx.mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
@@ -357,7 +359,15 @@ class CellSweepFunction(torch.autograd.Function):
         dm_depth = None if d_dmean is None else d_dmean[..., D - 1:]
         ds_depth = None if d_dstd is None else d_dstd[..., D - 1:]
 
-        for t in range(s.n_wavefronts - 1, -1, -1):
+        fused = ctx.fused_dims is not None and plan.fused_backward
+        if fused:
+            # ONE persistent launch for the whole reverse sweep (csrc/sweep.cu: sweep_bwd_kernel)
+            descs = [K.sweep_mlp_bwd_desc([w.contiguous() for w in m.W], m.H[0], m.H[1], m.Y, m.dX, m.dH[0], m.dH[1], m.dY)
+                     for m in (box_mlp, enc_mlp, z_mlp, obj_mlp)]
+            K.sweep_bwd(ctx.fused_dims, plan.order_dev, plan.starts_dev, plan.wf_pos_dev, s.offsets, x, z_where, eps_where,
+                        eps_attr, eps_depth, u_pres, wheel, plan.geom, descs, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd)
+
+        for t in range(s.n_wavefronts - 1 if not fused else -1, -1, -1):
             c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
             r0, r1 = c0 * B, c1 * B
             n = r1 - r0

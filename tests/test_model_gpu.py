@@ -12,12 +12,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused-sweep", "per-wavefront"])
+@pytest.mark.parametrize("fused", [(True, True), (True, False), (False, False)],
+                         ids=["fused-sweep", "fused-forward-only", "per-wavefront"])
 @pytest.mark.parametrize("name,step", [("tiny", 1), ("tiny", 1001), ("A", 1), ("A", 1001)])
 def test_model_matches_reference_golden(name, step, fused):
+    """The three launch modes of the cell sweep (one persistent kernel per direction / per-wavefront kernels + cuBLAS)
+    against golden vectors produced by the unmodified reference."""
     net = helpers.build_model(name, DEV)
     g = helpers.load_golden("model_%s_step%d.npz" % (name, step))
-    net._get_plan(torch.device(DEV, torch.cuda.current_device())).fused_forward = fused
+    plan = net._get_plan(torch.device(DEV, torch.cuda.current_device()))
+    plan.fused_forward, plan.fused_backward = fused
     helpers.check_model_against_golden(net, g, DEV)
 
 
@@ -181,7 +185,7 @@ def test_fused_forward_sweep_equals_per_wavefront_path(name, B):
     for fused in (True, False):
         net._plan = None
         net(x[:1], 1001)                    # builds the plan
-        net._plan.fused_forward = fused
+        net._plan.fused_forward = net._plan.fused_backward = fused
         net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)
         for p in net.parameters():
             p.grad = None
