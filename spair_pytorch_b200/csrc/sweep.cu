@@ -17,8 +17,9 @@ namespace spair {
 
 constexpr int kSwThreads = 512;     // 16 warps: the weight stream from L2 is latency bound, warps hide it
 constexpr int kSwRows = 16;        // padded rows per CTA and wavefront
-constexpr int kSwKC = 128;         // K-chunk of a layer whose input comes from global memory
+constexpr int kSwKC = 512;         // K-chunk of a layer whose input comes from global memory
 constexpr int kSwKCP = kSwKC + 4;  // padded chunk row (keeps float4 alignment, staggers banks)
+constexpr int kSwPart = kSwThreads * kSwRows;   // split-K partial sums: [K-split][row][column] = 8192 floats
 constexpr int kSwHP = 256 + 4;     // padded hidden row
 constexpr int kSwMaxG = 64;
 
@@ -92,70 +93,124 @@ __device__ __forceinline__ void dense_accumulate(float (&acc)[RG], const float* 
     }
 }
 
-template <int RG>
-__device__ void dense_layer_rg(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
-                               const int* __restrict__ grow, int nrows, float* chunk, float* out_smem,
-                               float* __restrict__ out_glob, bool relu) {
-    constexpr int NCOLP = kSwThreads * RG / kSwRows;      // threads = NCOLP columns x (kSwRows / RG) row groups
-    const int n = threadIdx.x % NCOLP;
-    const int row0 = (threadIdx.x / NCOLP) * RG;
-    const bool active = n < L.N && row0 < nrows;       // a row group made of padding rows only has nothing to do
-    float acc[RG];
-    const float bias = active ? __ldg(L.b + n) : 0.0f;
+// ---- split-K dense layer --------------------------------------------------------------------------------------
+// The 512 threads are NCOLP output columns x KS = 512 / NCOLP slices of the reduction index.  A thread accumulates
+// NR (<= 16) rows x 1 column over its K-slice, so a weight element is loaded ONCE per CTA and used for every row, and
+// the dependent load->FMA chain of a layer is KS times shorter than with one thread per column (the sweep is bound
+// by that chain: the CTA is alone on its SM).  Partial sums meet in shared memory; the epilogue adds the bias,
+// applies ReLU / the ReLU mask and stores to shared + global memory.
+template <int NR, int NCOLP>
+__device__ __forceinline__ void accumulate_slice(float (&acc)[NR], const float* __restrict__ W, int rowlen, int col,
+                                                 int wk0, int kc, int Kvalid, const float* __restrict__ xs, int stride) {
+    constexpr int KS = kSwThreads / NCOLP;
+    const int ks = threadIdx.x / NCOLP;
+    const int per = ((kc + KS * 8 - 1) / (KS * 8)) * 8;      // slice length, a multiple of 8
+    const int kb = ks * per, ke = min(kc, kb + per);
+    if (kb < ke) dense_accumulate<NR>(acc, W, rowlen, col, wk0 + kb, ke - kb, Kvalid, xs + kb, stride, 0);
+}
+
+template <int NR, int NCOLP>
+__device__ __forceinline__ void store_partials(const float (&acc)[NR], float* part) {
+    const int n = threadIdx.x % NCOLP, ks = threadIdx.x / NCOLP;
 #pragma unroll
-    for (int r = 0; r < RG; ++r) acc[r] = bias;
+    for (int r = 0; r < NR; ++r) part[(ks * kSwRows + r) * NCOLP + n] = acc[r];
+}
+
+// out[r][c0 + n] = act(bias + sum over K-slices); rows >= nr_comp are zero
+template <int NCOLP>
+__device__ __forceinline__ void finalize_columns(const float* part, const float* __restrict__ bias, int ncols_total, int c0,
+                                                 int nr_comp, int nrows, bool relu, const float* __restrict__ Hmask,
+                                                 const int* __restrict__ grow, float* out_smem, float* __restrict__ out_glob,
+                                                 int ld_out) {
+    constexpr int KS = kSwThreads / NCOLP;
+    for (int idx = threadIdx.x; idx < kSwRows * NCOLP; idx += kSwThreads) {
+        const int r = idx / NCOLP, n = idx % NCOLP, col = c0 + n;
+        if (col >= ncols_total) continue;
+        float v = 0.0f;
+        if (r < nr_comp) {
+            v = bias ? __ldg(bias + col) : 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) v += part[(ks * kSwRows + r) * NCOLP + n];
+            if (relu) v = fmaxf(v, 0.0f);
+        }
+        if (r < nrows) {
+            const size_t g = grow[r];
+            if (Hmask && !(Hmask[g * ncols_total + col] > 0.0f)) v = 0.0f;
+            out_glob[g * ld_out + col] = v;
+        }
+        if (out_smem) out_smem[r * kSwHP + col] = v;
+    }
+}
+
+// forward layer: out = act(in . Wt + b).  in_smem != nullptr: activations in shared memory [r][kSwHP]; otherwise the
+// input rows live in global memory (Xg) and are staged through `chunk` in slabs of kSwKC columns.
+template <int NR, int NCOLP>
+__device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
+                              const int* __restrict__ grow, int nrows, float* chunk, float* part, float* out_smem,
+                              float* __restrict__ out_glob, bool relu) {
+    const int n = threadIdx.x % NCOLP;
+    const bool active = n < L.N;
+    float acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
     if (in_smem) {
-        const int kc = (L.K + 3) & ~3;      // hidden rows are zero-padded to a multiple of 4
-        if (active) dense_accumulate<RG>(acc, L.Wt, L.N, n, 0, kc, L.K, in_smem, kSwHP, row0);
+        if (active) accumulate_slice<NR, NCOLP>(acc, L.Wt, L.N, n, 0, (L.K + 3) & ~3, L.K, in_smem, kSwHP);
     } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 16 warps == kSwRows: one warp stages one row
         for (int k0 = 0; k0 < L.K; k0 += kSwKC) {
             const int kc = min(kSwKC, L.K - k0);
             const int kcp = (kc + 3) & ~3;
-            __syncthreads();                 // previous chunk fully consumed
-            for (int idx = threadIdx.x; idx < kSwRows * kcp; idx += kSwThreads) {
-                const int r = idx / kcp, kk = idx - r * kcp;
-                chunk[r * kSwKCP + kk] = (r < nrows && kk < kc) ? Xg[(size_t)grow[r] * ldX + k0 + kk] : 0.0f;
+            __syncthreads();                 // previous slab fully consumed
+            {
+                const float* src = Xg + (size_t)grow[warp] * ldX + k0;
+                float* dst = chunk + warp * kSwKCP;
+                for (int kk = lane; kk < kcp; kk += 32) dst[kk] = (warp < nrows && kk < kc) ? src[kk] : 0.0f;
             }
             __syncthreads();
-            if (active) dense_accumulate<RG>(acc, L.Wt, L.N, n, k0, kcp, L.K, chunk, kSwKCP, row0);
+            if (active) accumulate_slice<NR, NCOLP>(acc, L.Wt, L.N, n, k0, kcp, L.K, chunk, kSwKCP);
         }
     }
-    if (active) {
-#pragma unroll
-        for (int r = 0; r < RG; ++r) {
-            const float v = relu ? fmaxf(acc[r], 0.0f) : acc[r];
-            const int row = row0 + r;
-            out_smem[row * kSwHP + n] = v;
-            if (row < nrows) out_glob[(size_t)grow[row] * L.N + n] = v;
-        }
-    }
-}
-
-__device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in_smem, const float* Xg, int ldX,
-                                            const int* grow, int nrows, float* chunk, float* out_smem, float* out_glob,
-                                            bool relu) {
-    // zero the padding columns the next layer's float4 reads may touch
-    for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + L.N + (idx & 3)] = 0.0f;
-    if (L.N <= 128) dense_layer_rg<4>(L, in_smem, Xg, ldX, grow, nrows, chunk, out_smem, out_glob, relu);     // 128 x 4
-    else dense_layer_rg<8>(L, in_smem, Xg, ldX, grow, nrows, chunk, out_smem, out_glob, relu);                // 256 x 2
+    store_partials<NR, NCOLP>(acc, part);
+    __syncthreads();
+    finalize_columns<NCOLP>(part, L.b, L.N, 0, NR, nrows, relu, nullptr, grow, out_smem, out_glob, L.N);
     __syncthreads();
 }
 
+__device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in_smem, const float* Xg, int ldX,
+                                            const int* grow, int nrows, float* chunk, float* part, float* out_smem,
+                                            float* out_glob, bool relu) {
+    // zero the padding columns the next layer's float4 reads may touch
+    for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + L.N + (idx & 3)] = 0.0f;
+    const int q = (nrows + 3) >> 2;         // rows actually computed, in groups of 4
+    if (L.N <= 128) {
+        if (q <= 1) dense_layer_t<4, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else if (q == 2) dense_layer_t<8, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else if (q == 3) dense_layer_t<12, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else dense_layer_t<16, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+    } else {
+        if (q <= 1) dense_layer_t<4, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else if (q == 2) dense_layer_t<8, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else if (q == 3) dense_layer_t<12, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        else dense_layer_t<16, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+    }
+}
+
 // three-layer MLP: X (global) -> H0 -> H1 -> Y ; result left in shared memory `y`
-__device__ __forceinline__ void mlp3(const SweepMLP& M, const int* grow, int nrows, float* chunk, float* ha, float* hb,
-                                     float* y) {
-    dense_layer(M.l[0], nullptr, M.X, M.ldX, grow, nrows, chunk, ha, M.H0, true);
-    dense_layer(M.l[1], ha, nullptr, 0, grow, nrows, chunk, hb, M.H1, true);
-    dense_layer(M.l[2], hb, nullptr, 0, grow, nrows, chunk, y, M.Y, false);
+__device__ __forceinline__ void mlp3(const SweepMLP& M, const int* grow, int nrows, float* chunk, float* part, float* ha,
+                                     float* hb, float* y) {
+    dense_layer(M.l[0], nullptr, M.X, M.ldX, grow, nrows, chunk, part, ha, M.H0, true);
+    dense_layer(M.l[1], ha, nullptr, 0, grow, nrows, chunk, part, hb, M.H1, true);
+    dense_layer(M.l[2], hb, nullptr, 0, grow, nrows, chunk, part, y, M.Y, false);
 }
 
 __device__ __forceinline__ int sw_box_slot(int k) { return k == 0 ? 1 : (k == 1 ? 0 : (k == 2 ? 3 : 2)); }
 
 __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p) {
-    static_assert(kSwThreads * 4 / kSwRows == 128 && kSwThreads * 8 / kSwRows == 256, "thread mapping of dense_layer_rg");
+    static_assert(kSwThreads / 32 == kSwRows, "one warp stages one input row");
     extern __shared__ __align__(16) float sm[];
     float* chunk = sm;                                  // [kSwRows][kSwKCP]
-    float* ha = chunk + kSwRows * kSwKCP;               // [kSwRows][kSwHP]
+    float* part = chunk + kSwRows * kSwKCP;             // [kSwPart] split-K partial sums
+    float* ha = part + kSwPart;                         // [kSwRows][kSwHP]
     float* hb = ha + kSwRows * kSwHP;
     float* y = hb + kSwRows * kSwHP;
     float* base_g = y + kSwRows * kSwHP;                // [kSwMaxG] normalised base grid of the glimpse
@@ -220,7 +275,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         // (dense_layer starts with a barrier before it reads the rows back)
 
         // ---- z_where: box network + box head (models.py:76-79, 322-381) ----
-        mlp3(p.box, grow, nrows, chunk, ha, hb, y);
+        mlp3(p.box, grow, nrows, chunk, part, ha, hb, y);
         for (int idx = threadIdx.x; idx < nrows * (4 + p.P); idx += kSwThreads) {
             const int r = idx / (4 + p.P), k = idx - r * (4 + p.P);
             const size_t g = grow[r];
@@ -279,7 +334,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
                 orow[c * GG + tt] = acc;
             }
         }
-        mlp3(p.enc, grow, nrows, chunk, ha, hb, y);
+        mlp3(p.enc, grow, nrows, chunk, part, ha, hb, y);
         for (int idx = threadIdx.x; idx < nrows * p.A; idx += kSwThreads) {
             const int r = idx / p.A, k = idx - r * p.A;
             const size_t g = grow[r];
@@ -296,7 +351,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         }
 
         // ---- z_depth (models.py:88-97) ----
-        mlp3(p.z, grow, nrows, chunk, ha, hb, y);
+        mlp3(p.z, grow, nrows, chunk, part, ha, hb, y);
         for (int idx = threadIdx.x; idx < nrows * (1 + p.P); idx += kSwThreads) {
             const int r = idx / (1 + p.P), k = idx - r * (1 + p.P);
             const size_t g = grow[r];
@@ -316,7 +371,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         }
 
         // ---- z_pres (models.py:100-105, 393-411) ----
-        mlp3(p.obj, grow, nrows, chunk, ha, hb, y);
+        mlp3(p.obj, grow, nrows, chunk, part, ha, hb, y);
         if (threadIdx.x < nrows) {
             const int r = threadIdx.x;
             const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
@@ -359,51 +414,51 @@ struct SweepBwdArgs {
     const float* d_dmean; const float* d_dstd;
 };
 
-// out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), columns processed in passes of 128
-__device__ void dense_bwd_layer(const float* __restrict__ W, int Nred, int Kout, const float* g_smem,
-                                const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows,
-                                float* out_smem, float* __restrict__ out_glob, int ld_out) {
-    constexpr int RG = 4, NCOLP = kSwThreads * RG / kSwRows;
-    const int row0 = (threadIdx.x / NCOLP) * RG;
+// out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), output columns in passes of 128, reduction split 4 ways
+template <int NR>
+__device__ void dense_bwd_layer_t(const float* __restrict__ W, int Nred, int Kout, const float* g_smem,
+                                  const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows, float* part,
+                                  float* out_smem, float* __restrict__ out_glob, int ld_out) {
+    constexpr int NCOLP = 128;
     const int kc = (Nred + 3) & ~3;
-    if (out_smem)
-        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + Kout + (idx & 3)] = 0.0f;
     for (int c0 = 0; c0 < Kout; c0 += NCOLP) {
         const int col = c0 + threadIdx.x % NCOLP;
-        if (col < Kout && row0 < nrows) {
-            float acc[RG];
+        float acc[NR];
 #pragma unroll
-            for (int r = 0; r < RG; ++r) acc[r] = 0.0f;
-            dense_accumulate<RG>(acc, W, Kout, col, 0, kc, Nred, g_smem, kSwHP, row0);
-#pragma unroll
-            for (int r = 0; r < RG; ++r) {
-                const int row = row0 + r;
-                float v = acc[r];
-                if (row < nrows) {
-                    const size_t g = grow[row];
-                    if (Hmask && !(Hmask[g * Kout + col] > 0.0f)) v = 0.0f;
-                    out_glob[g * ld_out + col] = v;
-                } else {
-                    v = 0.0f;
-                }
-                if (out_smem) out_smem[row * kSwHP + col] = v;
-            }
-        }
+        for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
+        if (col < Kout) accumulate_slice<NR, NCOLP>(acc, W, Kout, col, 0, kc, Nred, g_smem, kSwHP);
+        store_partials<NR, NCOLP>(acc, part);
+        __syncthreads();
+        finalize_columns<NCOLP>(part, nullptr, Kout, c0, NR, nrows, false, Hmask, grow, out_smem, out_glob, ld_out);
+        __syncthreads();
     }
-    __syncthreads();
+}
+
+__device__ __forceinline__ void dense_bwd_layer(const float* W, int Nred, int Kout, const float* g_smem, const float* Hmask,
+                                                const int* grow, int nrows, float* part, float* out_smem, float* out_glob,
+                                                int ld_out) {
+    if (out_smem)
+        for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + Kout + (idx & 3)] = 0.0f;
+    const int q = (nrows + 3) >> 2;
+    if (q <= 1) dense_bwd_layer_t<4>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+    else if (q == 2) dense_bwd_layer_t<8>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+    else if (q == 3) dense_bwd_layer_t<12>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+    else dense_bwd_layer_t<16>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
 }
 
 // dY (already in shared memory `gy` and in global M.dY) -> dH1 -> dH0 -> dX
-__device__ __forceinline__ void mlp3_bwd(const SweepMLPBwd& M, const int* grow, int nrows, float* gy, float* ga, float* gb) {
-    dense_bwd_layer(M.W[2], M.N[2], M.K[2], gy, M.H1, grow, nrows, ga, M.dH1, M.K[2]);
-    dense_bwd_layer(M.W[1], M.N[1], M.K[1], ga, M.H0, grow, nrows, gb, M.dH0, M.K[1]);
-    dense_bwd_layer(M.W[0], M.N[0], M.K[0], gb, nullptr, grow, nrows, nullptr, M.dX, M.ldX);
+__device__ __forceinline__ void mlp3_bwd(const SweepMLPBwd& M, const int* grow, int nrows, float* part, float* gy, float* ga,
+                                         float* gb) {
+    dense_bwd_layer(M.W[2], M.N[2], M.K[2], gy, M.H1, grow, nrows, part, ga, M.dH1, M.K[2]);
+    dense_bwd_layer(M.W[1], M.N[1], M.K[1], ga, M.H0, grow, nrows, part, gb, M.dH0, M.K[1]);
+    dense_bwd_layer(M.W[0], M.N[0], M.K[0], gb, nullptr, grow, nrows, part, nullptr, M.dX, M.ldX);
 }
 
 __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p) {
     static_assert(kSwThreads / 32 == kSwRows, "the glimpse gradient uses one warp per row");
     extern __shared__ __align__(16) float sm[];
-    float* gy = sm;                                     // [kSwRows][kSwHP] dY of the current network
+    float* part = sm;                                   // [kSwPart] split-K partial sums
+    float* gy = part + kSwPart;                         // [kSwRows][kSwHP] dY of the current network
     float* ga = gy + kSwRows * kSwHP;
     float* gb = ga + kSwRows * kSwHP;
     float* dcell = gb + kSwRows * kSwHP;                // [kSwRows][64] gradient through the lateral context
@@ -474,7 +529,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + 1] = gy[r * kSwHP + 2] = gy[r * kSwHP + 3] = 0.0f;
         }
         __syncthreads();
-        mlp3_bwd(p.obj, grow, nrows, gy, ga, gb);
+        mlp3_bwd(p.obj, grow, nrows, part, gy, ga, gb);
 
         // ---- z_depth (models.py:88-97) ----
         for (int idx = threadIdx.x; idx < kSwRows * (2 + p.P); idx += kSwThreads) {
@@ -501,7 +556,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 + p.P + (idx & 3)] = 0.0f;
         __syncthreads();
-        mlp3_bwd(p.z, grow, nrows, gy, ga, gb);
+        mlp3_bwd(p.z, grow, nrows, part, gy, ga, gb);
 
         // ---- z_what (models.py:83-85) ----
         for (int idx = threadIdx.x; idx < kSwRows * p.A; idx += kSwThreads) {
@@ -524,7 +579,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 * p.A + (idx & 3)] = 0.0f;
         __syncthreads();
-        mlp3_bwd(p.enc, grow, nrows, gy, ga, gb);
+        mlp3_bwd(p.enc, grow, nrows, part, gy, ga, gb);
 
         // ---- glimpse: d z_where (modules.py:216-273; the image has no gradient in the model) ----
         // one warp per row (kSwThreads / 32 == kSwRows): lanes stride over the texels, one butterfly reduction per row —
@@ -610,7 +665,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 8 + p.P + (idx & 3)] = 0.0f;
         __syncthreads();
-        mlp3_bwd(p.box, grow, nrows, gy, ga, gb);
+        mlp3_bwd(p.box, grow, nrows, part, gy, ga, gb);
     }
 }
 
@@ -656,7 +711,7 @@ extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, cons
     SPAIR_REQUIRE(a.z.l[0].K == d->F + CTX + d->P + 4 + d->A && a.z.l[2].N == 2 + d->P);
     SPAIR_REQUIRE(a.obj.l[0].K == a.z.l[0].K + 1 && a.obj.l[2].N == 1);
     a.out_box = box; a.z_where = z_where; a.attr = attr; a.depth = depth; a.pres = pres; a.dmean = dmean; a.dstd = dstd;
-    const size_t smem = sizeof(float) * (size_t)(kSwRows * kSwKCP + 3 * kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
+    const size_t smem = sizeof(float) * (size_t)(kSwRows * kSwKCP + kSwPart + 3 * kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
                         sizeof(int) * 3 * kSwRows;
     static bool attr_set = false;
     if (!attr_set) {
@@ -706,7 +761,8 @@ extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, cons
     SPAIR_REQUIRE(a.z.K[0] == d->F + CTX + d->P + 4 + d->A && a.z.N[2] == 2 + d->P && a.obj.K[0] == a.z.K[0] + 1 && a.obj.N[2] == 1);
     a.encX = nullptr; a.ld_encX = 0;
     a.d_zw = d_zw; a.d_attr = d_attr; a.d_depth = d_depth; a.d_pres = d_pres; a.d_dmean = d_dmean; a.d_dstd = d_dstd;
-    const size_t smem = sizeof(float) * (size_t)(3 * kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) + sizeof(int) * 3 * kSwRows;
+    const size_t smem = sizeof(float) * (size_t)(kSwPart + 3 * kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) +
+                        sizeof(int) * 3 * kSwRows;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(sweep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
