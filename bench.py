@@ -312,8 +312,15 @@ def run_ours(args):
         n_launch = K.launch_count() - n0 if launches_per_step is None else launches_per_step * steps
         return float(ms) / steps, n_launch, clk.summary()
 
-    if args.profile_step:       # for `ncu`: warm-up + the timed steps only (no e2e pass, no kernel microbench, no JSON)
-        timed(step_resident, args.steps, args.warmup)
+    if args.profile_step:       # for `ncu --profile-from-start off`: only the steps after warm-up are inside the
+        for i in range(args.warmup):            # cudaProfilerStart/Stop range (no e2e pass, no microbench, no JSON)
+            step_resident(i)
+        barrier()
+        torch.cuda.profiler.start()
+        for i in range(args.steps):
+            step_resident(args.warmup + i)
+        barrier()
+        torch.cuda.profiler.stop()
         return None
     ms_res, launches, clocks = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))

@@ -250,8 +250,8 @@ int spair_kl_bwd(const float* dmean, const float* dstd, const float* pres,
  * wavefront-major activation buffers (x, h0, h1, y of each MLP; row = position(cell)*B + b), so the
  * backward pass is unchanged.  The MLPs (reference modules.py:124-165: two ReLU hidden layers + a
  * linear output, multi-head outputs concatenated) are evaluated by the kernel itself in fp32 SIMT
- * FMAs from TRANSPOSED weights wt[k][n].  Limits: max_cells * ipc <= spair_sweep_max_rows(),
- * layer widths <= 256, G <= 64.
+ * FMAs from PACKED weights (spair_sweep_pack_weights below).  Limits: max_cells * ipc <=
+ * spair_sweep_max_rows(), layer widths <= 256, G <= 64.
  * ---------------------------------------------------------------------------------- */
 typedef struct spair_sweep_dims {
     int B, HW, Hc, Wc;      /* batch, cells */
@@ -261,8 +261,20 @@ typedef struct spair_sweep_dims {
     int n_wavefronts, max_cells, n_nb;
 } spair_sweep_dims;
 
+/* Packs nn.Linear weights w[n][k] (reference modules.py:124-165) for the two sweeps, all layers in one launch:
+ *   fwd [ceil(k/4)][n][4] : fwd[(g*n + col)*4 + j] = w[col][4g+j]   (reduction over k, one float4 per column and group)
+ *   bwd [ceil(n/4)][k][4] : bwd[(g*k + col)*4 + j] = w[4g+j][col]   (reduction over n)
+ * zero padded; either destination may be NULL; both must be 16-byte aligned; n_layers <= 16. */
+typedef struct spair_sweep_pack {
+    const float* w; int n, k;
+    float* fwd; float* bwd;
+} spair_sweep_pack;
+
+int spair_sweep_pack_weights(const spair_sweep_pack* layers /* host array, device pointers inside */, int n_layers,
+                             void* stream);
+
 typedef struct spair_sweep_mlp {
-    const float* wt[3];     /* transposed weights [k][n] of hidden0, hidden1, output */
+    const float* wt[3];     /* `fwd`-packed weights of hidden0, hidden1, output */
     const float* b[3];      /* biases [n] */
     int k[3], n[3];
     float* x; int ld_x;     /* [HW*B, ld_x] input rows; the kernel fills them */
@@ -286,13 +298,13 @@ int spair_sweep_fwd(const spair_sweep_dims* dims,        /* host */
                     void* stream);
 
 /* Backward of the fused sweep, same image partition, wavefronts in reverse order.  Reads the forward
- * activations (h0, h1, y of each MLP) and the UNtransposed weights w[n][k], writes dy / dh1 / dh0 / dx of every
+ * activations (h0, h1, y of each MLP) and the `bwd`-packed weights, writes dy / dh1 / dh0 / dx of every
  * row (wavefront-major; they feed the weight-gradient GEMMs and the feature / edge-element reductions done by
  * the caller).  d_* are the image-major gradients arriving from the renderer, the decoder and the KL terms
  * (any may be NULL).  Replaces spair_context_grad_gather, spair_pres_head_bwd, spair_normal_head_bwd x2,
  * spair_glimpse_bwd, spair_box_head_bwd, spair_relu_bwd and the per-wavefront dX GEMMs. */
 typedef struct spair_sweep_mlp_bwd {
-    const float* w[3];      /* weights as stored, [n][k], of hidden0, hidden1, output */
+    const float* w[3];      /* `bwd`-packed weights of hidden0, hidden1, output */
     int k[3], n[3];
     const float* h0; const float* h1; const float* y;   /* forward activations */
     float* dx; int ld_dx;   /* [HW*B, ld_dx] gradient wrt the input rows (written) */

@@ -5,8 +5,9 @@
 // them with block-level barriers only — no kernel boundary, no grid-wide synchronisation.  Per wavefront a CTA
 // handles R = n_cells * ipc <= 16 rows through context gather -> box MLP -> box head -> glimpse -> encoder MLP ->
 // attr head -> z MLP -> depth head -> obj MLP -> presence head.  The MLP layers are register-tiled SIMT dot
-// products: a thread owns one output column (and 8 or 16 rows), streams the TRANSPOSED weights Wt[k][n] from L2
-// with coalesced loads and reads the activations as 128-bit shared-memory broadcasts; each weight element is
+// products: a thread owns one output column, up to 16 rows and a slice of the reduction index; it streams PACKED
+// weights (four consecutive reduction indices of one column = one float4, spair_sweep_pack_weights) from L2 with
+// coalesced 128-bit loads and reads the activations as 128-bit shared-memory broadcasts; each weight element is
 // fetched once per CTA and wavefront and reused for all rows.  All activations are also written to the same
 // wavefront-major global buffers the unfused path uses, so the backward pass (and the weight-gradient GEMMs) are
 // unchanged.  This replaces ~27 launches per wavefront (12 cuBLAS GEMMs of <= 1536 rows, 8 elementwise, 6 head
@@ -24,7 +25,7 @@ constexpr int kSwHP = 256 + 4;     // padded hidden row
 constexpr int kSwMaxG = 64;
 
 struct SweepLayer {
-    const float* Wt;   // [K][N] transposed weight
+    const float4* Wp;  // [ceil(K/4)][N] packed weight: Wp[g][n] = W[n][4g .. 4g+3], zero padded
     const float* b;    // [N]
     int K, N;
 };
@@ -48,65 +49,67 @@ struct SweepFwdArgs {
     float* out_box; float* z_where; float* attr; float* depth; float* pres; float* dmean; float* dstd;
 };
 
-// ---- one dense layer over the CTA's rows -----------------------------------------------------------------------
-// in_smem != nullptr : input activations resident in shared memory, in_smem[r * kSwHP + k]
-// otherwise          : input rows in global memory X[grow[r] * ldX + k], staged through `chunk` in K-chunks
-// out_smem[r * kSwHP + n] receives the result (ReLU applied if relu), out_glob[grow[r] * N + n] as well.
-template <int RG>
-__device__ __forceinline__ void fma_rows4(float (&acc)[RG], const float* __restrict__ xp, int xs_stride, const float* w) {
-#pragma unroll
-    for (int r = 0; r < RG; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(xp + r * xs_stride);
-        acc[r] = fmaf(w[0], x.x, acc[r]);
-        acc[r] = fmaf(w[1], x.y, acc[r]);
-        acc[r] = fmaf(w[2], x.z, acc[r]);
-        acc[r] = fmaf(w[3], x.w, acc[r]);
-    }
-}
-
-// acc[r] += sum_k Wt[k0 + k][n] * xs[row0 + r][k] for k in [0, kc), kc a multiple of 4 (xs zero-padded), weights
-// beyond K treated as 0.  Main loop: 8 unguarded coalesced weight loads issued before use, unrolled twice, so ~16
-// L2 requests per thread are in flight (the layer streams its weights once per CTA and wavefront).
-template <int RG>
-__device__ __forceinline__ void dense_accumulate(float (&acc)[RG], const float* __restrict__ Wt, int N, int n, int k0,
-                                                 int kc, int K, const float* __restrict__ xs, int xs_stride, int row0) {
-    const float* wp = Wt + k0 * N + n;
-    const float* xp = xs + row0 * xs_stride;
-    const int k_real = min(kc, K - k0);
-    const int k_main = k_real & ~7;
-    int k = 0;
-#pragma unroll 2
-    for (; k < k_main; k += 8) {
-        float w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __ldg(wp + i * N);
-        wp += 8 * N;
-        fma_rows4<RG>(acc, xp + k, xs_stride, w);
-        fma_rows4<RG>(acc, xp + k + 4, xs_stride, w + 4);
-    }
-    for (; k < kc; k += 4) {
-        float w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = (k + i < k_real) ? __ldg(wp + i * N) : 0.0f;
-        wp += 4 * N;
-        fma_rows4<RG>(acc, xp + k, xs_stride, w);
-    }
-}
-
 // ---- split-K dense layer --------------------------------------------------------------------------------------
 // The 512 threads are NCOLP output columns x KS = 512 / NCOLP slices of the reduction index.  A thread accumulates
-// NR (<= 16) rows x 1 column over its K-slice, so a weight element is loaded ONCE per CTA and used for every row, and
+// NR (<= 16) rows x 1 column over its slice, so a weight element is loaded ONCE per CTA and used for every row, and
 // the dependent load->FMA chain of a layer is KS times shorter than with one thread per column (the sweep is bound
 // by that chain: the CTA is alone on its SM).  Partial sums meet in shared memory; the epilogue adds the bias,
 // applies ReLU / the ReLU mask and stores to shared + global memory.
+
+// acc[r] += w . x[r][0..3] for all rows; rows are taken in pairs so consecutive FMAs hit different accumulators
+template <int NR>
+__device__ __forceinline__ void fma_group(float (&acc)[NR], const float* __restrict__ xp, int stride, const float4 w) {
+#pragma unroll
+    for (int r = 0; r < NR; r += 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xp + r * stride);
+        const float4 x1 = *reinterpret_cast<const float4*>(xp + (r + 1) * stride);
+        acc[r] = fmaf(w.x, x0.x, acc[r]);
+        acc[r + 1] = fmaf(w.x, x1.x, acc[r + 1]);
+        acc[r] = fmaf(w.y, x0.y, acc[r]);
+        acc[r + 1] = fmaf(w.y, x1.y, acc[r + 1]);
+        acc[r] = fmaf(w.z, x0.z, acc[r]);
+        acc[r + 1] = fmaf(w.z, x1.z, acc[r + 1]);
+        acc[r] = fmaf(w.w, x0.w, acc[r]);
+        acc[r + 1] = fmaf(w.w, x1.w, acc[r + 1]);
+    }
+}
+
+// acc[r] += sum over groups g in [0, ng) of P[g0 + g][col] . xs[r][4g .. 4g+3].  Weight loads are software
+// pipelined in batches of four float4 (the next batch is in flight while the current one is consumed).
+template <int NR>
+__device__ __forceinline__ void accumulate_packed(float (&acc)[NR], const float4* __restrict__ P, int ncols, int col, int g0,
+                                                  int ng, const float* __restrict__ xs, int stride) {
+    const float4* wp = P + (size_t)g0 * ncols + col;
+    const float* xp = xs;
+    int g = 0;
+#pragma unroll 1
+    for (; g + 4 <= ng; g += 4) {
+        const float4 c0 = __ldg(wp), c1 = __ldg(wp + ncols), c2 = __ldg(wp + 2 * ncols), c3 = __ldg(wp + 3 * ncols);
+        wp += 4 * ncols;
+        fma_group<NR>(acc, xp, stride, c0);
+        fma_group<NR>(acc, xp + 4, stride, c1);
+        fma_group<NR>(acc, xp + 8, stride, c2);
+        fma_group<NR>(acc, xp + 12, stride, c3);
+        xp += 16;
+    }
+#pragma unroll 1
+    for (; g < ng; ++g) {
+        const float4 w = __ldg(wp);
+        wp += ncols;
+        fma_group<NR>(acc, xp, stride, w);
+        xp += 4;
+    }
+}
+
+// this thread's slice of `ng` reduction groups (xs points at group 0, P row g0 is group 0)
 template <int NR, int NCOLP>
-__device__ __forceinline__ void accumulate_slice(float (&acc)[NR], const float* __restrict__ W, int rowlen, int col,
-                                                 int wk0, int kc, int Kvalid, const float* __restrict__ xs, int stride) {
+__device__ __forceinline__ void accumulate_slice(float (&acc)[NR], const float4* __restrict__ P, int ncols, int col, int g0,
+                                                 int ng, const float* __restrict__ xs, int stride) {
     constexpr int KS = kSwThreads / NCOLP;
     const int ks = threadIdx.x / NCOLP;
-    const int per = ((kc + KS * 8 - 1) / (KS * 8)) * 8;      // slice length, a multiple of 8
-    const int kb = ks * per, ke = min(kc, kb + per);
-    if (kb < ke) dense_accumulate<NR>(acc, W, rowlen, col, wk0 + kb, ke - kb, Kvalid, xs + kb, stride, 0);
+    const int per = (ng + KS - 1) / KS;
+    const int gb = ks * per, ge = min(ng, gb + per);
+    if (gb < ge) accumulate_packed<NR>(acc, P, ncols, col, g0 + gb, ge - gb, xs + 4 * gb, stride);
 }
 
 template <int NR, int NCOLP>
@@ -142,7 +145,7 @@ __device__ __forceinline__ void finalize_columns(const float* part, const float*
     }
 }
 
-// forward layer: out = act(in . Wt + b).  in_smem != nullptr: activations in shared memory [r][kSwHP]; otherwise the
+// forward layer: out = act(in . W^T + b).  in_smem != nullptr: activations in shared memory [r][kSwHP]; otherwise the
 // input rows live in global memory (Xg) and are staged through `chunk` in slabs of kSwKC columns.
 template <int NR, int NCOLP>
 __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
@@ -154,7 +157,7 @@ __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const f
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
     if (in_smem) {
-        if (active) accumulate_slice<NR, NCOLP>(acc, L.Wt, L.N, n, 0, (L.K + 3) & ~3, L.K, in_smem, kSwHP);
+        if (active) accumulate_slice<NR, NCOLP>(acc, L.Wp, L.N, n, 0, (L.K + 3) >> 2, in_smem, kSwHP);
     } else {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 16 warps == kSwRows: one warp stages one row
         for (int k0 = 0; k0 < L.K; k0 += kSwKC) {
@@ -167,7 +170,7 @@ __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const f
                 for (int kk = lane; kk < kcp; kk += 32) dst[kk] = (warp < nrows && kk < kc) ? src[kk] : 0.0f;
             }
             __syncthreads();
-            if (active) accumulate_slice<NR, NCOLP>(acc, L.Wt, L.N, n, k0, kcp, L.K, chunk, kSwKCP);
+            if (active) accumulate_slice<NR, NCOLP>(acc, L.Wp, L.N, n, k0 >> 2, kcp >> 2, chunk, kSwKCP);
         }
     }
     store_partials<NR, NCOLP>(acc, part);
@@ -389,12 +392,12 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
 // arrives through the lateral context comes from cells of later wavefronts of the SAME image, i.e. from rows this
 // CTA has already written.  Per wavefront: context-gradient gather -> presence head -> obj MLP (dX chain) -> depth
 // head -> z MLP -> attr head -> encoder MLP -> glimpse (d z_where) -> box head -> box MLP.  A backward layer
-// dX = dY . W is the same register-tiled dot product as the forward with the UNtransposed weight W[n][k] (reduction
+// dX = dY . W is the same register-tiled dot product as the forward with the weight packed along n (reduction
 // over n, coalesced over k) and a ReLU-mask epilogue.  dY / dH / dX of every row are written to the wavefront-major
 // global buffers: the 13 weight gradients stay one large cuBLAS GEMM each over all rows, after the sweep.
 // =================================================================================================================
 struct SweepMLPBwd {
-    const float* W[3];     // [N][K] weights as stored (hidden0, hidden1, output)
+    const float4* W[3];    // [ceil(N/4)][K] packed weights: W[g][k] = (w[4g][k] .. w[4g+3][k]), zero padded
     int K[3], N[3];
     const float* H0; const float* H1; const float* Y;   // forward activations
     float* dX; int ldX; float* dH0; float* dH1; float* dY;
@@ -416,17 +419,17 @@ struct SweepBwdArgs {
 
 // out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), output columns in passes of 128, reduction split 4 ways
 template <int NR>
-__device__ void dense_bwd_layer_t(const float* __restrict__ W, int Nred, int Kout, const float* g_smem,
+__device__ void dense_bwd_layer_t(const float4* __restrict__ W, int Nred, int Kout, const float* g_smem,
                                   const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows, float* part,
                                   float* out_smem, float* __restrict__ out_glob, int ld_out) {
     constexpr int NCOLP = 128;
-    const int kc = (Nred + 3) & ~3;
+    const int ng = (Nred + 3) >> 2;
     for (int c0 = 0; c0 < Kout; c0 += NCOLP) {
         const int col = c0 + threadIdx.x % NCOLP;
         float acc[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
-        if (col < Kout) accumulate_slice<NR, NCOLP>(acc, W, Kout, col, 0, kc, Nred, g_smem, kSwHP);
+        if (col < Kout) accumulate_slice<NR, NCOLP>(acc, W, Kout, col, 0, ng, g_smem, kSwHP);
         store_partials<NR, NCOLP>(acc, part);
         __syncthreads();
         finalize_columns<NCOLP>(part, nullptr, Kout, c0, NR, nrows, false, Hmask, grow, out_smem, out_glob, ld_out);
@@ -434,7 +437,7 @@ __device__ void dense_bwd_layer_t(const float* __restrict__ W, int Nred, int Kou
     }
 }
 
-__device__ __forceinline__ void dense_bwd_layer(const float* W, int Nred, int Kout, const float* g_smem, const float* Hmask,
+__device__ __forceinline__ void dense_bwd_layer(const float4* W, int Nred, int Kout, const float* g_smem, const float* Hmask,
                                                 const int* grow, int nrows, float* part, float* out_smem, float* out_glob,
                                                 int ld_out) {
     if (out_smem)
@@ -669,16 +672,64 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
     }
 }
 
+// ---- weight packing for the two sweeps ----------------------------------------------------------------------------
+constexpr int kPackMaxLayers = 16;
+struct PackArgs {
+    const float* W[kPackMaxLayers];
+    float4* fwd[kPackMaxLayers];
+    float4* bwd[kPackMaxLayers];
+    int N[kPackMaxLayers], K[kPackMaxLayers];
+};
+
+__global__ void __launch_bounds__(256) sweep_pack_kernel(PackArgs p) {
+    const int l = blockIdx.y;
+    const float* __restrict__ W = p.W[l];
+    const int N = p.N[l], K = p.K[l];
+    const int nf = ((K + 3) >> 2) * N, nbk = ((N + 3) >> 2) * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nbk; i += gridDim.x * blockDim.x) {
+        float v[4];
+        if (i < nf) {
+            const int g = i / N, n = i - g * N;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (4 * g + j < K) ? __ldg(W + (size_t)n * K + 4 * g + j) : 0.0f;
+            if (p.fwd[l]) p.fwd[l][i] = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            const int q = i - nf, g = q / K, k = q - g * K;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (4 * g + j < N) ? __ldg(W + (size_t)(4 * g + j) * K + k) : 0.0f;
+            if (p.bwd[l]) p.bwd[l][q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 }  // namespace spair
 
 using namespace spair;
+
+extern "C" int spair_sweep_pack_weights(const spair_sweep_pack* layers, int n_layers, void* stream) {
+    SPAIR_REQUIRE(layers && n_layers >= 1 && n_layers <= kPackMaxLayers);
+    PackArgs a;
+    int most = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const spair_sweep_pack& L = layers[l];
+        SPAIR_REQUIRE(L.w && L.n > 0 && L.k > 0 && (L.fwd || L.bwd));
+        SPAIR_REQUIRE(((uintptr_t)L.fwd % 16) == 0 && ((uintptr_t)L.bwd % 16) == 0);
+        a.W[l] = L.w; a.fwd[l] = reinterpret_cast<float4*>(L.fwd); a.bwd[l] = reinterpret_cast<float4*>(L.bwd);
+        a.N[l] = L.n; a.K[l] = L.k;
+        most = max(most, ((L.k + 3) / 4) * L.n + ((L.n + 3) / 4) * L.k);
+    }
+    dim3 grid(min((most + 255) / 256, 64), n_layers);
+    sweep_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    SPAIR_LAUNCH_CHECK();
+}
 
 // Host-side description of one MLP for spair_sweep_fwd (mirrors the C struct in include/spair_b200.h)
 static bool to_mlp(const spair_sweep_mlp* m, SweepMLP& out) {
     if (!m || !m->x || !m->h0 || !m->h1 || !m->y) return false;
     for (int i = 0; i < 3; ++i) {
         if (!m->wt[i] || !m->b[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
-        out.l[i] = SweepLayer{m->wt[i], m->b[i], m->k[i], m->n[i]};
+        if ((uintptr_t)m->wt[i] % 16) return false;
+        out.l[i] = SweepLayer{reinterpret_cast<const float4*>(m->wt[i]), m->b[i], m->k[i], m->n[i]};
     }
     if (m->k[1] != m->n[0] || m->k[2] != m->n[1] || m->ld_x < m->k[0]) return false;
     out.X = m->x; out.ldX = m->ld_x; out.H0 = m->h0; out.H1 = m->h1; out.Y = m->y;
@@ -727,7 +778,8 @@ static bool to_mlp_bwd(const spair_sweep_mlp_bwd* m, SweepMLPBwd& out) {
     if (!m || !m->h0 || !m->h1 || !m->y || !m->dx || !m->dh0 || !m->dh1 || !m->dy) return false;
     for (int i = 0; i < 3; ++i) {
         if (!m->w[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
-        out.W[i] = m->w[i]; out.K[i] = m->k[i]; out.N[i] = m->n[i];
+        if ((uintptr_t)m->w[i] % 16) return false;
+        out.W[i] = reinterpret_cast<const float4*>(m->w[i]); out.K[i] = m->k[i]; out.N[i] = m->n[i];
     }
     if (m->k[1] != m->n[0] || m->k[2] != m->n[1] || m->ld_dx < m->k[0]) return false;
     out.H0 = m->h0; out.H1 = m->h1; out.Y = m->y; out.dX = m->dx; out.ldX = m->ld_dx;

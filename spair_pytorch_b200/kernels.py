@@ -40,6 +40,12 @@ class SweepMLP(ctypes.Structure):
                 ("y", ctypes.c_void_p)]
 
 
+class SweepPack(ctypes.Structure):
+    """``spair_sweep_pack`` of include/spair_b200.h."""
+    _fields_ = [("w", ctypes.c_void_p), ("n", ctypes.c_int), ("k", ctypes.c_int), ("fwd", ctypes.c_void_p),
+                ("bwd", ctypes.c_void_p)]
+
+
 class SweepMLPBwd(ctypes.Structure):
     """``spair_sweep_mlp_bwd`` of include/spair_b200.h."""
     _fields_ = [("w", ctypes.c_void_p * 3), ("k", ctypes.c_int * 3), ("n", ctypes.c_int * 3),
@@ -77,6 +83,7 @@ _SIGNATURES = {
     "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
     "spair_sweep_max_rows": [],
+    "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
     "spair_sweep_bwd": [_P] * 23 + [_P],
 }
@@ -274,12 +281,36 @@ def sweep_max_rows() -> int:
     return lib().spair_sweep_max_rows()
 
 
-def sweep_mlp_desc(wts, biases, X, H0, H1, Y) -> SweepMLP:
-    """wts: transposed weights [K,N] (contiguous) of the two hidden layers and the output layer."""
+class PackedSweepWeights:
+    """Both packed layouts of a list of ``nn.Linear`` weights [N, K] in ONE flat buffer, filled by one launch
+    (``spair_sweep_pack_weights``).  ``fwd[i]`` / ``bwd[i]`` are views; keep this object alive while kernels use them."""
+
+    def __init__(self, weights):
+        for w in weights:
+            require_cuda(w, "weight")
+        self.shapes = [(int(w.shape[0]), int(w.shape[1])) for w in weights]
+        sizes = [(((k + 3) // 4) * 4 * n, ((n + 3) // 4) * 4 * k) for n, k in self.shapes]
+        self.flat = torch.empty(sum(a + b for a, b in sizes), device=weights[0].device, dtype=torch.float32)
+        self.fwd, self.bwd = [], []
+        off = 0
+        for a, b in sizes:
+            self.fwd.append(self.flat[off:off + a])
+            self.bwd.append(self.flat[off + a:off + a + b])
+            off += a + b
+        self._sources = [_contig(w.detach(), "weight") for w in weights]
+        arr = (SweepPack * len(weights))()
+        for i, w in enumerate(self._sources):
+            arr[i].w, arr[i].n, arr[i].k = _ptr(w), self.shapes[i][0], self.shapes[i][1]
+            arr[i].fwd, arr[i].bwd = _ptr(self.fwd[i]), _ptr(self.bwd[i])
+        _check(lib().spair_sweep_pack_weights(arr, len(weights), _stream()), "spair_sweep_pack_weights")
+
+
+def sweep_mlp_desc(packed, first, biases, X, H0, H1, Y) -> SweepMLP:
+    """packed: PackedSweepWeights; layers first .. first+2 are the two hidden layers and the output layer."""
     m = SweepMLP()
-    for i, (w, b) in enumerate(zip(wts, biases)):
-        m.wt[i], m.b[i] = _ptr(_contig(w, "wt")), _ptr(_contig(b, "bias"))
-        m.k[i], m.n[i] = w.shape[0], w.shape[1]
+    for i, b in enumerate(biases):
+        m.wt[i], m.b[i] = _ptr(packed.fwd[first + i]), _ptr(_contig(b, "bias"))
+        m.n[i], m.k[i] = packed.shapes[first + i]
     m.x, m.ld_x, m.h0, m.h1, m.y = _ptr(_contig(X, "X")), X.shape[1], _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), \
         _ptr(_contig(Y, "Y"))
     return m
@@ -297,12 +328,12 @@ def sweep_fwd(dims: SweepDims, order, starts, offsets, image, feat, edge, eps_wh
                                  _stream()), "spair_sweep_fwd")
 
 
-def sweep_mlp_bwd_desc(ws, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBwd:
-    """ws: weights as stored [N,K] (contiguous) of the two hidden layers and the output layer."""
+def sweep_mlp_bwd_desc(packed, first, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBwd:
+    """packed: PackedSweepWeights; layers first .. first+2 are the two hidden layers and the output layer."""
     m = SweepMLPBwd()
-    for i, w in enumerate(ws):
-        m.w[i] = _ptr(_contig(w, "weight"))
-        m.n[i], m.k[i] = w.shape[0], w.shape[1]
+    for i in range(3):
+        m.w[i] = _ptr(packed.bwd[first + i])
+        m.n[i], m.k[i] = packed.shapes[first + i]
     m.h0, m.h1, m.y = _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), _ptr(_contig(Y, "Y"))
     m.dx, m.ld_dx = _ptr(_contig(dX, "dX")), dX.shape[1]
     m.dh0, m.dh1, m.dy = _ptr(_contig(dH0, "dH0")), _ptr(_contig(dH1, "dH1")), _ptr(_contig(dY, "dY"))

@@ -295,8 +295,8 @@ class CellSweepFunction(torch.autograd.Function):
             ipc = max(1, min(2, max_rows // s.max_cells))
             dims = K.SweepDims(B=B, HW=HW, Hc=s.Hc, Wc=s.Wc, F=F, A=A, P=P, C=plan.C, Ih=plan.Ih, Iw=plan.Iw, G=G, ipc=ipc,
                                n_wavefronts=s.n_wavefronts, max_cells=s.max_cells, n_nb=len(s.offsets))
-            wts = [[w.t().contiguous() for w in m.W] for m in mlps]     # kept alive until the launch is enqueued
-            descs = [K.sweep_mlp_desc(wt, m.b, m.X, m.H[0], m.H[1], m.Y) for wt, m in zip(wts, mlps)]
+            packed = K.PackedSweepWeights([w for m in mlps for w in m.W])   # both layouts, one launch; kept for backward
+            descs = [K.sweep_mlp_desc(packed, 3 * i, m.b, m.X, m.H[0], m.H[1], m.Y) for i, m in enumerate(mlps)]
             K.sweep_fwd(dims, plan.order_dev, plan.starts_dev, s.offsets, x, feat, edge, eps_where, eps_attr, eps_depth,
                         u_pres, plan.geom, descs, box, z_where, attr, depth, pres, dmean, dstd)
 
@@ -320,6 +320,7 @@ class CellSweepFunction(torch.autograd.Function):
             K.pres_head_fwd(obj_mlp.Y[r0:r1], u_pres, cells, B, HW, pres)
 
         ctx.fused_dims = dims if fused else None
+        ctx.packed_weights = packed if fused else None
         ctx.plan = plan
         plan.last_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)      # inspection hook for tests (no copy)
         ctx.mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
@@ -362,8 +363,9 @@ class CellSweepFunction(torch.autograd.Function):
         fused = ctx.fused_dims is not None and plan.fused_backward
         if fused:
             # ONE persistent launch for the whole reverse sweep (csrc/sweep.cu: sweep_bwd_kernel)
-            descs = [K.sweep_mlp_bwd_desc([w.contiguous() for w in m.W], m.H[0], m.H[1], m.Y, m.dX, m.dH[0], m.dH[1], m.dY)
-                     for m in (box_mlp, enc_mlp, z_mlp, obj_mlp)]
+            packed = ctx.packed_weights
+            descs = [K.sweep_mlp_bwd_desc(packed, 3 * i, m.H[0], m.H[1], m.Y, m.dX, m.dH[0], m.dH[1], m.dY)
+                     for i, m in enumerate((box_mlp, enc_mlp, z_mlp, obj_mlp))]
             K.sweep_bwd(ctx.fused_dims, plan.order_dev, plan.starts_dev, plan.wf_pos_dev, s.offsets, x, z_where, eps_where,
                         eps_attr, eps_depth, u_pres, wheel, plan.geom, descs, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd)
 
