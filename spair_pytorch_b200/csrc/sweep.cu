@@ -20,9 +20,18 @@ constexpr int kSwThreads = 512;     // 16 warps: the weight stream from L2 is la
 constexpr int kSwRows = 16;        // padded rows per CTA and wavefront
 constexpr int kSwKC = 512;         // K-chunk of a layer whose input comes from global memory
 constexpr int kSwKCP = kSwKC + 4;  // padded chunk row (keeps float4 alignment, staggers banks)
-constexpr int kSwPart = kSwThreads * kSwRows;   // split-K partial sums: [K-split][row][column] = 8192 floats
+constexpr int kSwPart = 2 * kSwThreads * kSwRows;   // split-K partial sums: [K-split][row][column] = 16384 floats
 constexpr int kSwHP = 256 + 4;     // padded hidden row
 constexpr int kSwMaxG = 64;
+
+#ifdef SW_TIMING
+__device__ long long g_sw_timing[64];
+#define SW_T0() long long sw_t_ = clock64()
+#define SW_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); g_sw_timing[i] += n_ - sw_t_; sw_t_ = n_; } } while (0)
+#else
+#define SW_T0()
+#define SW_MARK(i)
+#endif
 
 struct SweepLayer {
     const float4* Wp;  // [ceil(K/4)][N] packed weight: Wp[g][n] = W[n][4g .. 4g+3], zero padded
@@ -50,73 +59,107 @@ struct SweepFwdArgs {
 };
 
 // ---- split-K dense layer --------------------------------------------------------------------------------------
-// The 512 threads are NCOLP output columns x KS = 512 / NCOLP slices of the reduction index.  A thread accumulates
-// NR (<= 16) rows x 1 column over its slice, so a weight element is loaded ONCE per CTA and used for every row, and
-// the dependent load->FMA chain of a layer is KS times shorter than with one thread per column (the sweep is bound
-// by that chain: the CTA is alone on its SM).  Partial sums meet in shared memory; the epilogue adds the bias,
-// applies ReLU / the ReLU mask and stores to shared + global memory.
+// The 512 threads are NCOLP / 2 column pairs x KS = 1024 / NCOLP slices of the reduction index.  A thread accumulates
+// NR (<= 16) rows x 2 columns over its slice: a weight element is loaded ONCE per CTA and used for every row, an
+// activation (128-bit shared-memory broadcast) feeds 8 FMAs, and the dependent load->FMA chain of a layer is KS
+// times shorter than with one thread per column (the sweep is latency bound: the CTA is alone on its SM).  Partial
+// sums meet in shared memory; the epilogue adds the bias, applies ReLU / the ReLU mask and stores to shared + global
+// memory.
 
-// acc[r] += w . x[r][0..3] for all rows; rows are taken in pairs so consecutive FMAs hit different accumulators
+// acc[r] += w . x[r][0..3] for all rows and both columns of the thread: one 128-bit shared-memory broadcast feeds 8 FMAs
 template <int NR>
-__device__ __forceinline__ void fma_group(float (&acc)[NR], const float* __restrict__ xp, int stride, const float4 w) {
+__device__ __forceinline__ void fma_group2(float (&a)[NR], float (&b)[NR], const float* __restrict__ xp, int stride,
+                                           const float4 wa, const float4 wb) {
 #pragma unroll
-    for (int r = 0; r < NR; r += 2) {
-        const float4 x0 = *reinterpret_cast<const float4*>(xp + r * stride);
-        const float4 x1 = *reinterpret_cast<const float4*>(xp + (r + 1) * stride);
-        acc[r] = fmaf(w.x, x0.x, acc[r]);
-        acc[r + 1] = fmaf(w.x, x1.x, acc[r + 1]);
-        acc[r] = fmaf(w.y, x0.y, acc[r]);
-        acc[r + 1] = fmaf(w.y, x1.y, acc[r + 1]);
-        acc[r] = fmaf(w.z, x0.z, acc[r]);
-        acc[r + 1] = fmaf(w.z, x1.z, acc[r + 1]);
-        acc[r] = fmaf(w.w, x0.w, acc[r]);
-        acc[r + 1] = fmaf(w.w, x1.w, acc[r + 1]);
+    for (int r = 0; r < NR; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(xp + r * stride);
+        a[r] = fmaf(wa.x, x.x, a[r]);
+        b[r] = fmaf(wb.x, x.x, b[r]);
+        a[r] = fmaf(wa.y, x.y, a[r]);
+        b[r] = fmaf(wb.y, x.y, b[r]);
+        a[r] = fmaf(wa.z, x.z, a[r]);
+        b[r] = fmaf(wb.z, x.z, b[r]);
+        a[r] = fmaf(wa.w, x.w, a[r]);
+        b[r] = fmaf(wb.w, x.w, b[r]);
     }
 }
 
-// acc[r] += sum over groups g in [0, ng) of P[g0 + g][col] . xs[r][4g .. 4g+3].  Weight loads are software
-// pipelined in batches of four float4 (the next batch is in flight while the current one is consumed).
+// a[r] += sum over groups g in [0, ng) of P[g0 + g][colA] . xs[r][4g .. 4g+3] (b: colB)
 template <int NR>
-__device__ __forceinline__ void accumulate_packed(float (&acc)[NR], const float4* __restrict__ P, int ncols, int col, int g0,
-                                                  int ng, const float* __restrict__ xs, int stride) {
-    const float4* wp = P + (size_t)g0 * ncols + col;
+__device__ __forceinline__ void accumulate_packed2(float (&a)[NR], float (&b)[NR], const float4* __restrict__ P, int ncols,
+                                                   int colA, int colB, int g0, int ng, const float* __restrict__ xs, int stride) {
+    const float4* wa = P + (size_t)g0 * ncols + colA;
+    const int dB = colB - colA;
     const float* xp = xs;
     int g = 0;
 #pragma unroll 1
     for (; g + 4 <= ng; g += 4) {
-        const float4 c0 = __ldg(wp), c1 = __ldg(wp + ncols), c2 = __ldg(wp + 2 * ncols), c3 = __ldg(wp + 3 * ncols);
-        wp += 4 * ncols;
-        fma_group<NR>(acc, xp, stride, c0);
-        fma_group<NR>(acc, xp + 4, stride, c1);
-        fma_group<NR>(acc, xp + 8, stride, c2);
-        fma_group<NR>(acc, xp + 12, stride, c3);
+        const float4 a0 = __ldg(wa), a1 = __ldg(wa + ncols), a2 = __ldg(wa + 2 * ncols), a3 = __ldg(wa + 3 * ncols);
+        const float4 b0 = __ldg(wa + dB), b1 = __ldg(wa + ncols + dB), b2 = __ldg(wa + 2 * ncols + dB), b3 = __ldg(wa + 3 * ncols + dB);
+        wa += 4 * ncols;
+        fma_group2<NR>(a, b, xp, stride, a0, b0);
+        fma_group2<NR>(a, b, xp + 4, stride, a1, b1);
+        fma_group2<NR>(a, b, xp + 8, stride, a2, b2);
+        fma_group2<NR>(a, b, xp + 12, stride, a3, b3);
         xp += 16;
     }
 #pragma unroll 1
     for (; g < ng; ++g) {
-        const float4 w = __ldg(wp);
-        wp += ncols;
-        fma_group<NR>(acc, xp, stride, w);
+        const float4 a0 = __ldg(wa), b0 = __ldg(wa + dB);
+        wa += ncols;
+        fma_group2<NR>(a, b, xp, stride, a0, b0);
         xp += 4;
     }
 }
 
-// this thread's slice of `ng` reduction groups (xs points at group 0, P row g0 is group 0)
+// Thread mapping of one pass over NCOLP output columns: thread -> column pair (n, n + NCOLP/2), K-slice ks of KS
+template <int NCOLP>
+struct SliceMap {
+    static constexpr int kHalf = NCOLP / 2;
+    static constexpr int KS = kSwThreads / kHalf;
+    static_assert(KS * kSwRows * NCOLP <= kSwPart, "partial-sum buffer");
+};
+
+// this thread's slice of `ng` reduction groups (xs points at group 0, P row g0 is group 0); c0 = first column of the pass
 template <int NR, int NCOLP>
-__device__ __forceinline__ void accumulate_slice(float (&acc)[NR], const float4* __restrict__ P, int ncols, int col, int g0,
-                                                 int ng, const float* __restrict__ xs, int stride) {
-    constexpr int KS = kSwThreads / NCOLP;
-    const int ks = threadIdx.x / NCOLP;
-    const int per = (ng + KS - 1) / KS;
+__device__ __forceinline__ void accumulate_slice(float (&a)[NR], float (&b)[NR], const float4* __restrict__ P, int ncols, int c0,
+                                                 int g0, int ng, const float* __restrict__ xs, int stride) {
+    using M = SliceMap<NCOLP>;
+    const int n = threadIdx.x % M::kHalf, ks = threadIdx.x / M::kHalf;
+    const int colA = c0 + n;
+    if (colA >= ncols) return;
+    const int colB = (colA + M::kHalf < ncols) ? colA + M::kHalf : colA;     // no second column: recompute the first
+    const int per = (ng + M::KS - 1) / M::KS;
     const int gb = ks * per, ge = min(ng, gb + per);
-    if (gb < ge) accumulate_packed<NR>(acc, P, ncols, col, g0 + gb, ge - gb, xs + 4 * gb, stride);
+    if (gb < ge) accumulate_packed2<NR>(a, b, P, ncols, colA, colB, g0 + gb, ge - gb, xs + 4 * gb, stride);
 }
 
 template <int NR, int NCOLP>
-__device__ __forceinline__ void store_partials(const float (&acc)[NR], float* part) {
-    const int n = threadIdx.x % NCOLP, ks = threadIdx.x / NCOLP;
+__device__ __forceinline__ void store_partials(const float (&a)[NR], const float (&b)[NR], float* part) {
+    using M = SliceMap<NCOLP>;
+    const int n = threadIdx.x % M::kHalf, ks = threadIdx.x / M::kHalf;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) part[(ks * kSwRows + r) * NCOLP + n] = acc[r];
+    for (int r = 0; r < NR; ++r) {
+        part[(ks * kSwRows + r) * NCOLP + n] = a[r];
+        part[(ks * kSwRows + r) * NCOLP + n + M::kHalf] = b[r];
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Issued BEFORE the accumulation: pulls the bias / ReLU-mask words finalize_columns will read into L1, so that their
+// L2 / HBM latency overlaps the weight stream instead of following it.
+template <int NCOLP>
+__device__ __forceinline__ void prefetch_epilogue(const float* __restrict__ bias, const float* __restrict__ Hmask,
+                                                  int ncols_total, int c0, int nrows, const int* __restrict__ grow) {
+    if (bias && threadIdx.x * 32 < NCOLP && c0 + threadIdx.x * 32 < ncols_total) prefetch_l1(bias + c0 + threadIdx.x * 32);
+    if (Hmask) {
+        constexpr int kLines = NCOLP / 32;                      // 128-byte lines per row and pass
+        for (int idx = threadIdx.x; idx < nrows * kLines; idx += kSwThreads) {
+            const int r = idx / kLines, col = c0 + (idx % kLines) * 32;
+            if (col < ncols_total) prefetch_l1(Hmask + (size_t)grow[r] * ncols_total + col);
+        }
+    }
 }
 
 // out[r][c0 + n] = act(bias + sum over K-slices); rows >= nr_comp are zero
@@ -125,7 +168,7 @@ __device__ __forceinline__ void finalize_columns(const float* part, const float*
                                                  int nr_comp, int nrows, bool relu, const float* __restrict__ Hmask,
                                                  const int* __restrict__ grow, float* out_smem, float* __restrict__ out_glob,
                                                  int ld_out) {
-    constexpr int KS = kSwThreads / NCOLP;
+    constexpr int KS = SliceMap<NCOLP>::KS;
     for (int idx = threadIdx.x; idx < kSwRows * NCOLP; idx += kSwThreads) {
         const int r = idx / NCOLP, n = idx % NCOLP, col = c0 + n;
         if (col >= ncols_total) continue;
@@ -151,13 +194,13 @@ template <int NR, int NCOLP>
 __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
                               const int* __restrict__ grow, int nrows, float* chunk, float* part, float* out_smem,
                               float* __restrict__ out_glob, bool relu) {
-    const int n = threadIdx.x % NCOLP;
-    const bool active = n < L.N;
-    float acc[NR];
+    SW_T0();
+    prefetch_epilogue<NCOLP>(L.b, nullptr, L.N, 0, nrows, grow);
+    float a[NR], b[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0f;
     if (in_smem) {
-        if (active) accumulate_slice<NR, NCOLP>(acc, L.Wp, L.N, n, 0, (L.K + 3) >> 2, in_smem, kSwHP);
+        accumulate_slice<NR, NCOLP>(a, b, L.Wp, L.N, 0, 0, (L.K + 3) >> 2, in_smem, kSwHP);
     } else {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 16 warps == kSwRows: one warp stages one row
         for (int k0 = 0; k0 < L.K; k0 += kSwKC) {
@@ -170,13 +213,16 @@ __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const f
                 for (int kk = lane; kk < kcp; kk += 32) dst[kk] = (warp < nrows && kk < kc) ? src[kk] : 0.0f;
             }
             __syncthreads();
-            if (active) accumulate_slice<NR, NCOLP>(acc, L.Wp, L.N, n, k0 >> 2, kcp >> 2, chunk, kSwKCP);
+            accumulate_slice<NR, NCOLP>(a, b, L.Wp, L.N, 0, k0 >> 2, kcp >> 2, chunk, kSwKCP);
         }
     }
-    store_partials<NR, NCOLP>(acc, part);
+    SW_MARK(20);
+    store_partials<NR, NCOLP>(a, b, part);
     __syncthreads();
+    SW_MARK(21);
     finalize_columns<NCOLP>(part, L.b, L.N, 0, NR, nrows, relu, nullptr, grow, out_smem, out_glob, L.N);
     __syncthreads();
+    SW_MARK(22);
 }
 
 __device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in_smem, const float* Xg, int ldX,
@@ -201,9 +247,13 @@ __device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in
 // three-layer MLP: X (global) -> H0 -> H1 -> Y ; result left in shared memory `y`
 __device__ __forceinline__ void mlp3(const SweepMLP& M, const int* grow, int nrows, float* chunk, float* part, float* ha,
                                      float* hb, float* y) {
+    SW_T0();
     dense_layer(M.l[0], nullptr, M.X, M.ldX, grow, nrows, chunk, part, ha, M.H0, true);
+    SW_MARK(10);
     dense_layer(M.l[1], ha, nullptr, 0, grow, nrows, chunk, part, hb, M.H1, true);
+    SW_MARK(11);
     dense_layer(M.l[2], hb, nullptr, 0, grow, nrows, chunk, part, y, M.Y, false);
+    SW_MARK(12);
 }
 
 __device__ __forceinline__ int sw_box_slot(int k) { return k == 0 ? 1 : (k == 1 ? 0 : (k == 2 ? 3 : 2)); }
@@ -231,6 +281,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
     const int GG = p.G * p.G;
     for (int j = threadIdx.x; j < p.G; j += kSwThreads) base_g[j] = base_coord(j, p.G);
 
+    SW_T0();
     for (int t = 0; t < p.n_wavefronts; ++t) {
         const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
         const int nrows = n_cells * n_img;
@@ -250,6 +301,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
 
         // ---- L0: lateral context -> input columns [0, F+CTX) of the three networks (models.py:73,76) ----
         const int width = p.F + CTX;
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < nrows * width; idx += kSwThreads) {
             const int r = idx / width, col = idx - r * width;
             const int b = rimg[r], cell = rcell[r];
@@ -276,9 +328,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
             p.obj.X[g * p.obj.ldX + col] = v;
         }
         // (dense_layer starts with a barrier before it reads the rows back)
+        SW_MARK(0);
 
         // ---- z_where: box network + box head (models.py:76-79, 322-381) ----
         mlp3(p.box, grow, nrows, chunk, part, ha, hb, y);
+        SW_MARK(1);
         for (int idx = threadIdx.x; idx < nrows * (4 + p.P); idx += kSwThreads) {
             const int r = idx / (4 + p.P), k = idx - r * (4 + p.P);
             const size_t g = grow[r];
@@ -312,8 +366,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
             p.obj.X[g * p.obj.ldX + c_box + slot] = bval;
         }
         __syncthreads();
+        SW_MARK(2);
 
         // ---- z_what: glimpse (modules.py:216-273, border padding) -> encoder input rows ----
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < nrows * GG; idx += kSwThreads) {
             const int r = idx / GG, tt = idx - r * GG;
             const int i = tt / p.G, j = tt - i * p.G;
@@ -337,7 +393,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
                 orow[c * GG + tt] = acc;
             }
         }
+        SW_MARK(3);
         mlp3(p.enc, grow, nrows, chunk, part, ha, hb, y);
+        SW_MARK(4);
         for (int idx = threadIdx.x; idx < nrows * p.A; idx += kSwThreads) {
             const int r = idx / p.A, k = idx - r * p.A;
             const size_t g = grow[r];
@@ -354,7 +412,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         }
 
         // ---- z_depth (models.py:88-97) ----
+        SW_MARK(5);
         mlp3(p.z, grow, nrows, chunk, part, ha, hb, y);
+        SW_MARK(6);
         for (int idx = threadIdx.x; idx < nrows * (1 + p.P); idx += kSwThreads) {
             const int r = idx / (1 + p.P), k = idx - r * (1 + p.P);
             const size_t g = grow[r];
@@ -374,7 +434,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         }
 
         // ---- z_pres (models.py:100-105, 393-411) ----
+        SW_MARK(7);
         mlp3(p.obj, grow, nrows, chunk, part, ha, hb, y);
+        SW_MARK(8);
         if (threadIdx.x < nrows) {
             const int r = threadIdx.x;
             const size_t o = (size_t)rimg[r] * p.HW + rcell[r];
@@ -417,23 +479,26 @@ struct SweepBwdArgs {
     const float* d_dmean; const float* d_dstd;
 };
 
-// out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), output columns in passes of 128, reduction split 4 ways
-template <int NR>
+// out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), output columns in passes of 128, reduction split 8 ways
+template <int NR, int NCOLP>
 __device__ void dense_bwd_layer_t(const float4* __restrict__ W, int Nred, int Kout, const float* g_smem,
                                   const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows, float* part,
                                   float* out_smem, float* __restrict__ out_glob, int ld_out) {
-    constexpr int NCOLP = 128;
     const int ng = (Nred + 3) >> 2;
     for (int c0 = 0; c0 < Kout; c0 += NCOLP) {
-        const int col = c0 + threadIdx.x % NCOLP;
-        float acc[NR];
+        SW_T0();
+        prefetch_epilogue<NCOLP>(nullptr, Hmask, Kout, c0, nrows, grow);
+        float a[NR], b[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
-        if (col < Kout) accumulate_slice<NR, NCOLP>(acc, W, Kout, col, 0, ng, g_smem, kSwHP);
-        store_partials<NR, NCOLP>(acc, part);
+        for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0f;
+        accumulate_slice<NR, NCOLP>(a, b, W, Kout, c0, 0, ng, g_smem, kSwHP);
+        SW_MARK(40);
+        store_partials<NR, NCOLP>(a, b, part);
         __syncthreads();
+        SW_MARK(41);
         finalize_columns<NCOLP>(part, nullptr, Kout, c0, NR, nrows, false, Hmask, grow, out_smem, out_glob, ld_out);
         __syncthreads();
+        SW_MARK(42);
     }
 }
 
@@ -443,10 +508,20 @@ __device__ __forceinline__ void dense_bwd_layer(const float4* W, int Nred, int K
     if (out_smem)
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + Kout + (idx & 3)] = 0.0f;
     const int q = (nrows + 3) >> 2;
-    if (q <= 1) dense_bwd_layer_t<4>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
-    else if (q == 2) dense_bwd_layer_t<8>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
-    else if (q == 3) dense_bwd_layer_t<12>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
-    else dense_bwd_layer_t<16>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+#ifndef SW_BWD_WIDE
+#define SW_BWD_WIDE 1
+#endif
+    if (SW_BWD_WIDE && Kout > 128) {       // wide outputs: 256 columns per pass, reduction split 4 ways
+        if (q <= 1) dense_bwd_layer_t<4, 256>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else if (q == 2) dense_bwd_layer_t<8, 256>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else if (q == 3) dense_bwd_layer_t<12, 256>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else dense_bwd_layer_t<16, 256>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+    } else {                                // 128 columns per pass, reduction split 8 ways
+        if (q <= 1) dense_bwd_layer_t<4, 128>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else if (q == 2) dense_bwd_layer_t<8, 128>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else if (q == 3) dense_bwd_layer_t<12, 128>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+        else dense_bwd_layer_t<16, 128>(W, Nred, Kout, g_smem, Hmask, grow, nrows, part, out_smem, out_glob, ld_out);
+    }
 }
 
 // dY (already in shared memory `gy` and in global M.dY) -> dH1 -> dH0 -> dX
@@ -481,6 +556,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
     const float keep = 1.0f - p.wheel[0];
     for (int j = threadIdx.x; j < p.G; j += kSwThreads) base_g[j] = base_coord(j, p.G);
 
+    SW_T0();
     for (int t = p.n_wavefronts - 1; t >= 0; --t) {
         const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
         const int nrows = n_cells * n_img;
@@ -532,7 +608,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + 1] = gy[r * kSwHP + 2] = gy[r * kSwHP + 3] = 0.0f;
         }
         __syncthreads();
+        SW_MARK(30);
         mlp3_bwd(p.obj, grow, nrows, part, gy, ga, gb);
+        SW_MARK(31);
 
         // ---- z_depth (models.py:88-97) ----
         for (int idx = threadIdx.x; idx < kSwRows * (2 + p.P); idx += kSwThreads) {
@@ -559,7 +637,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 + p.P + (idx & 3)] = 0.0f;
         __syncthreads();
+        SW_MARK(32);
         mlp3_bwd(p.z, grow, nrows, part, gy, ga, gb);
+        SW_MARK(33);
 
         // ---- z_what (models.py:83-85) ----
         for (int idx = threadIdx.x; idx < kSwRows * p.A; idx += kSwThreads) {
@@ -582,7 +662,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 * p.A + (idx & 3)] = 0.0f;
         __syncthreads();
+        SW_MARK(34);
         mlp3_bwd(p.enc, grow, nrows, part, gy, ga, gb);
+        SW_MARK(35);
 
         // ---- glimpse: d z_where (modules.py:216-273; the image has no gradient in the model) ----
         // one warp per row (kSwThreads / 32 == kSwRows): lanes stride over the texels, one butterfly reduction per row —
@@ -595,6 +677,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
                 const float4 zw = *reinterpret_cast<const float4*>(p.z_where + o * 4);
                 const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
                 const float* grow_e = p.enc.dX + (size_t)grow[r] * p.enc.ldX;
+#pragma unroll 4
                 for (int tt = lane; tt < GG; tt += 32) {
                     const int i = tt / p.G, j = tt - i * p.G;
                     float ix = unnormalize(affine_coord(base_g[j], A.ax, A.cx), 0.5f * (float)p.Iw);
@@ -627,6 +710,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             if (lane == 0) { dzw[r * 4 + 0] = a0; dzw[r * 4 + 1] = a1; dzw[r * 4 + 2] = a2; dzw[r * 4 + 3] = a3; }
         }
         __syncthreads();
+        SW_MARK(38);
 
         // ---- z_where: box head (models.py:322-381) ----
         for (int idx = threadIdx.x; idx < kSwRows * (8 + p.P); idx += kSwThreads) {
@@ -668,7 +752,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 8 + p.P + (idx & 3)] = 0.0f;
         __syncthreads();
+        SW_MARK(36);
         mlp3_bwd(p.box, grow, nrows, part, gy, ga, gb);
+        SW_MARK(37);
     }
 }
 
@@ -737,6 +823,17 @@ static bool to_mlp(const spair_sweep_mlp* m, SweepMLP& out) {
 }
 
 extern "C" int spair_sweep_max_rows(void) { return kSwRows; }
+
+#ifdef SW_TIMING
+// debug builds only (-DSW_TIMING): per-phase clock64 totals of CTA 0, read and cleared
+extern "C" int spair_debug_sweep_timing(long long* out64) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out64, g_sw_timing, sizeof(long long) * 64);
+    long long zero[64] = {0};
+    cudaMemcpyToSymbol(g_sw_timing, zero, sizeof(zero));
+    return 0;
+}
+#endif
 
 extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
                                const float* image, const float* feat, const float* edge, const float* eps_where,
