@@ -186,6 +186,13 @@ class SweepPlan:
     def ctx_dim(self):
         return len(self.schedule.offsets) * self.E
 
+    def side_streams(self, device, n):
+        """Streams the backward pass forks the independent weight-gradient GEMMs to (created once per plan)."""
+        pool = self.__dict__.setdefault("_side_streams", [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=device))
+        return pool[:n]
+
     def to(self, device):
         s = self.schedule
         self.order_dev = torch.from_numpy(np.ascontiguousarray(s.order)).to(device=device, dtype=torch.int32)
@@ -231,11 +238,20 @@ class _ManualMLP:
             g = self.dH[l][r0:r1]
         torch.mm(g, self.W[0], out=self.dX[r0:r1])
 
+    def alloc_weight_grads(self):
+        """Outputs of ``weight_grads`` (allocated by the caller on ITS stream, filled on a side stream)."""
+        dev = self.X.device
+        self.dW = [torch.empty_like(w) for w in self.W]
+        self.db = [torch.empty(w.shape[0], device=dev, dtype=torch.float32) for w in self.W]
+
     def weight_grads(self):
         """One GEMM per layer over all rows: dW = dY^T X, db = column sums."""
         inputs = [self.X] + self.H
         grads = self.dH + [self.dY]
-        return [g.t().mm(i) for g, i in zip(grads, inputs)], [g.sum(0) for g in grads]
+        for g, i, dW, db in zip(grads, inputs, self.dW, self.db):
+            torch.mm(g.t(), i, out=dW)
+            torch.sum(g, 0, out=db)
+        return self.dW, self.db
 
 
 class CellSweepFunction(torch.autograd.Function):
@@ -408,9 +424,31 @@ class CellSweepFunction(torch.autograd.Function):
         n_nb = len(s.offsets)
         d_edge = (d_in[:, :, F:].reshape(HW, B, n_nb, E) * plan.missing_dev[:, None, :, None]).sum((0, 1, 2))
 
+        # ---- weight gradients: 12 skinny GEMMs (<= 256 x 784 outputs, reduction over all HW*B rows).  cuBLAS runs each
+        # as a split-K grid of ~70 CTAs, half of the 148 SMs, so the four networks go to four streams and overlap
+        # (forked from / joined to the current stream with events, which CUDA-graph capture records as parallel branches).
+        all_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
+        for mlp in all_mlps:
+            mlp.alloc_weight_grads()
+        if x.is_cuda:
+            cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            sides = plan.side_streams(x.device, len(all_mlps) - 1)
+            for mlp, st in zip(all_mlps[1:], sides):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    mlp.weight_grads()
+            all_mlps[0].weight_grads()
+            for st in sides:
+                cur.wait_stream(st)
+        else:
+            for mlp in all_mlps:
+                mlp.weight_grads()
+
         grads = []
         for mlp, n_heads, head_sizes in ((box_mlp, 2, (8, P)), (enc_mlp, 1, None), (z_mlp, 2, (2, P)), (obj_mlp, 1, None)):
-            dWs, dbs = mlp.weight_grads()
+            dWs, dbs = mlp.dW, mlp.db
             for dW, db in zip(dWs[:-1], dbs[:-1]):
                 grads += [dW, db]
             if n_heads == 1:
