@@ -182,31 +182,36 @@ def kernel_roofline(net, x, steps=20):
         out[name] = {"ms": ms, "bytes": nbytes, "achieved": gbs, "frac": gbs / peak}
     dom = max(out, key=lambda k: out[k]["ms"])       # dominant of the glimpse / render kernels BASELINE's metric names
     # the fused cell sweep: ONE persistent launch per direction holding all 31 wavefronts x 4 three-layer MLPs (fp32 SIMT
-    # GEMM chains, not HBM work) — reported with its FLOP rate next to the HBM-bound kernels
+    # dot products on <= 16 rows per CTA: latency / issue bound, not HBM work) — reported with its FLOP rate next to
+    # the HBM-bound kernels.  Timed with CUDA events placed directly around the two launches inside the operator.
     from spair_pytorch_b200 import ops
     plan = net._plan
-    with torch.no_grad():
-        feat = net.backbone(x)
-        noise = net._draw_noise(B, HW, dev)
-        st = net.prepare_step(STEP0, dev)
-        sweep_args = (plan, x, feat, net.virtual_edge_element, *noise, st.wheel, *net._sweep_params())
-        for _ in range(3):
-            ops.CellSweepFunction.apply(*sweep_args)
-        times = []
-        for _ in range(steps):
-            flush.fill_(1.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.CellSweepFunction.apply(*sweep_args)
-            e1.record()
-            e1.synchronize()
-            times.append(e0.elapsed_time(e1))
+    sweep_ms = {"fwd": [], "bwd": []}
+    feat = net.backbone(x).detach().requires_grad_(True)
+    noise = net._draw_noise(B, HW, dev)
+    st = net.prepare_step(STEP0, dev)
+    sweep_args = (plan, x, feat, net.virtual_edge_element, *noise, st.wheel, *net._sweep_params())
+    for it in range(3 + steps):
+        flush.fill_(1.0)
+        ops.SWEEP_EVENTS = {}
+        outs = ops.CellSweepFunction.apply(*sweep_args)
+        torch.autograd.backward([o.sum() for o in outs[:4]], inputs=[feat])
+        torch.cuda.synchronize()
+        ev, ops.SWEEP_EVENTS = ops.SWEEP_EVENTS, None
+        if it >= 3:
+            for k in sweep_ms:
+                if k in ev:
+                    sweep_ms[k].append(ev[k][0].elapsed_time(ev[k][1]))
     macs = sum(w.shape[0] * w.shape[1] for m in plan.last_mlps for w in m.W)
-    sweep_ms = statistics.mean(times)
-    out["sweep_fwd"] = {"ms": sweep_ms, "flops": 2 * macs * N, "achieved_tflops": 2 * macs * N / (sweep_ms * 1e-3) / 1e12,
-                        "note": "fused forward cell sweep (%s): context + 4 MLPs + heads + glimpse for all wavefronts in one "
-                                "launch, incl. its 12 weight transposes; fp32 SIMT FMAs (strict fp32: tensor cores not usable)"
-                                % ("persistent kernel" if plan.fused_forward else "per-wavefront launches")}
+    fp32_peak = 148 * 128 * 2 * 1.92e9 / 1e12          # SIMT FMA peak at the 1.92 GHz boost clock, TFLOP/s
+    for k, label in (("fwd", "sweep_fwd"), ("bwd", "sweep_bwd")):
+        if sweep_ms[k]:
+            ms = statistics.mean(sweep_ms[k])
+            tf = 2 * macs * N / (ms * 1e-3) / 1e12
+            out[label] = {"ms": ms, "flops": 2 * macs * N, "achieved_tflops": tf, "fp32_simt_peak_tflops": fp32_peak,
+                          "frac_of_fp32_simt_peak": tf / fp32_peak,
+                          "note": "persistent fused cell sweep (%s): context + 4 MLPs + heads + glimpse for all wavefronts "
+                                  "in one launch; fp32 SIMT FMAs, <= 16 rows per CTA and wavefront" % k}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
     # kernels at this shape (profiles/r01_warp_kernels_final_full.md; B=256, C=1, I=128, 121 cells, G=28)
     ncu_traffic = {"render_bwd": 228623872 + 159112192, "render_fwd": 201631488 + 24653056,

@@ -24,6 +24,20 @@ import torch
 from . import kernels as K
 from .schedule import WavefrontSchedule
 
+# bench.py sets this to a dict to have the two persistent sweep launches bracketed with CUDA events on the launching
+# stream: {"fwd": (start, end), "bwd": (start, end)}.  None (the default) records nothing.
+SWEEP_EVENTS: Optional[dict] = None
+
+
+def _timed_launch(name, fn, *args):
+    if SWEEP_EVENTS is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(*args)
+    e1.record()
+    SWEEP_EVENTS[name] = (e0, e1)
+
 
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.contiguous()
@@ -313,8 +327,8 @@ class CellSweepFunction(torch.autograd.Function):
                                n_wavefronts=s.n_wavefronts, max_cells=s.max_cells, n_nb=len(s.offsets))
             packed = K.PackedSweepWeights([w for m in mlps for w in m.W])   # both layouts, one launch; kept for backward
             descs = [K.sweep_mlp_desc(packed, 3 * i, m.b, m.X, m.H[0], m.H[1], m.Y) for i, m in enumerate(mlps)]
-            K.sweep_fwd(dims, plan.order_dev, plan.starts_dev, s.offsets, x, feat, edge, eps_where, eps_attr, eps_depth,
-                        u_pres, plan.geom, descs, box, z_where, attr, depth, pres, dmean, dstd)
+            _timed_launch("fwd", K.sweep_fwd, dims, plan.order_dev, plan.starts_dev, s.offsets, x, feat, edge, eps_where,
+                          eps_attr, eps_depth, u_pres, plan.geom, descs, box, z_where, attr, depth, pres, dmean, dstd)
 
         for t in range(s.n_wavefronts if not fused else 0):
             c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
@@ -382,8 +396,9 @@ class CellSweepFunction(torch.autograd.Function):
             packed = ctx.packed_weights
             descs = [K.sweep_mlp_bwd_desc(packed, 3 * i, m.H[0], m.H[1], m.Y, m.dX, m.dH[0], m.dH[1], m.dY)
                      for i, m in enumerate((box_mlp, enc_mlp, z_mlp, obj_mlp))]
-            K.sweep_bwd(ctx.fused_dims, plan.order_dev, plan.starts_dev, plan.wf_pos_dev, s.offsets, x, z_where, eps_where,
-                        eps_attr, eps_depth, u_pres, wheel, plan.geom, descs, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd)
+            _timed_launch("bwd", K.sweep_bwd, ctx.fused_dims, plan.order_dev, plan.starts_dev, plan.wf_pos_dev, s.offsets, x,
+                          z_where, eps_where, eps_attr, eps_depth, u_pres, wheel, plan.geom, descs, d_zw, d_attr, d_depth,
+                          d_pres, d_dmean, d_dstd)
 
         for t in range(s.n_wavefronts - 1 if not fused else -1, -1, -1):
             c0, c1 = int(s.starts[t]), int(s.starts[t + 1])
