@@ -190,8 +190,8 @@ __device__ __forceinline__ void finalize_columns(const float* part, const float*
 
 // forward layer: out = act(in . W^T + b).  in_smem != nullptr: activations in shared memory [r][kSwHP]; otherwise the
 // input rows live in global memory (Xg) and are staged through `chunk` in slabs of kSwKC columns.
-template <int NR, int NCOLP>
-__device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const float* __restrict__ Xg, int ldX,
+template <int NR, int NCOLP, bool GLOBAL_IN>
+__device__ __noinline__ void dense_layer_t(const SweepLayer L, const float* in_smem, const float* __restrict__ Xg, int ldX,
                               const int* __restrict__ grow, int nrows, float* chunk, float* part, float* out_smem,
                               float* __restrict__ out_glob, bool relu) {
     SW_T0();
@@ -199,7 +199,7 @@ __device__ void dense_layer_t(const SweepLayer& L, const float* in_smem, const f
     float a[NR], b[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0f;
-    if (in_smem) {
+    if (!GLOBAL_IN) {
         accumulate_slice<NR, NCOLP>(a, b, L.Wp, L.N, 0, 0, (L.K + 3) >> 2, in_smem, kSwHP);
     } else {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 16 warps == kSwRows: one warp stages one row
@@ -231,17 +231,23 @@ __device__ __forceinline__ void dense_layer(const SweepLayer& L, const float* in
     // zero the padding columns the next layer's float4 reads may touch
     for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) out_smem[(idx >> 2) * kSwHP + L.N + (idx & 3)] = 0.0f;
     const int q = (nrows + 3) >> 2;         // rows actually computed, in groups of 4
+#define SW_DISPATCH(NRV, NCV)                                                                                              \
+    do {                                                                                                                   \
+        if (in_smem) dense_layer_t<NRV, NCV, false>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu); \
+        else dense_layer_t<NRV, NCV, true>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);         \
+    } while (0)
     if (L.N <= 128) {
-        if (q <= 1) dense_layer_t<4, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else if (q == 2) dense_layer_t<8, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else if (q == 3) dense_layer_t<12, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else dense_layer_t<16, 128>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        if (q <= 1) SW_DISPATCH(4, 128);
+        else if (q == 2) SW_DISPATCH(8, 128);
+        else if (q == 3) SW_DISPATCH(12, 128);
+        else SW_DISPATCH(16, 128);
     } else {
-        if (q <= 1) dense_layer_t<4, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else if (q == 2) dense_layer_t<8, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else if (q == 3) dense_layer_t<12, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
-        else dense_layer_t<16, 256>(L, in_smem, Xg, ldX, grow, nrows, chunk, part, out_smem, out_glob, relu);
+        if (q <= 1) SW_DISPATCH(4, 256);
+        else if (q == 2) SW_DISPATCH(8, 256);
+        else if (q == 3) SW_DISPATCH(12, 256);
+        else SW_DISPATCH(16, 256);
     }
+#undef SW_DISPATCH
 }
 
 // three-layer MLP: X (global) -> H0 -> H1 -> Y ; result left in shared memory `y`
@@ -481,7 +487,7 @@ struct SweepBwdArgs {
 
 // out[r][c] = sum_n g[r][n] * W[n][c] (* (Hmask[r][c] > 0)), output columns in passes of 128, reduction split 8 ways
 template <int NR, int NCOLP>
-__device__ void dense_bwd_layer_t(const float4* __restrict__ W, int Nred, int Kout, const float* g_smem,
+__device__ __noinline__ void dense_bwd_layer_t(const float4* __restrict__ W, int Nred, int Kout, const float* g_smem,
                                   const float* __restrict__ Hmask, const int* __restrict__ grow, int nrows, float* part,
                                   float* out_smem, float* __restrict__ out_glob, int ld_out) {
     const int ng = (Nred + 3) >> 2;

@@ -395,3 +395,20 @@ def test_invalid_arguments_are_rejected_not_launched():
                      (2.0, 0.1, 5.0), torch.zeros(1, 1, 64, 64, device=DEV), torch.zeros(1, 64, 64, device=DEV), None, None)
     with pytest.raises(k.SpairKernelError):
         k.glimpse_fwd(torch.zeros(1, 1, 8, 8), torch.zeros(1, 4), None, 1, 1, 4, 4, torch.zeros(1, 16))   # CPU tensors
+
+
+@pytest.mark.parametrize("shapes", [[(100, 324), (100, 100), (108, 100)], [(1, 100), (256, 784), (7, 5)]])
+def test_sweep_weight_packing_is_exact(shapes):
+    """spair_sweep_pack_weights: fwd[(g*N + n)*4 + j] = W[n][4g+j], bwd[(g*K + k)*4 + j] = W[4g+j][k], zero padded."""
+    rs = gen(5)
+    ws = [torch.randn(n, k, generator=rs) for n, k in shapes]
+    packed = K().PackedSweepWeights([w.to(DEV) for w in ws])
+    for w, f, b in zip(ws, packed.fwd, packed.bwd):
+        n, k = w.shape
+        k4, n4 = (k + 3) // 4, (n + 3) // 4
+        wf = torch.zeros(n, 4 * k4)
+        wf[:, :k] = w
+        assert torch.equal(f.cpu().view(k4, n, 4), wf.view(n, k4, 4).permute(1, 0, 2)), "forward layout"
+        wb = torch.zeros(4 * n4, k)
+        wb[:n] = w
+        assert torch.equal(b.cpu().view(n4, k, 4), wb.view(n4, 4, k).permute(0, 2, 1)), "backward layout"
