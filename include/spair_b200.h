@@ -324,6 +324,22 @@ int spair_sweep_bwd(const spair_sweep_dims* dims, const int* order, const int* s
                     const float* d_dmean, const float* d_dstd,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Backbone stem (caller side of the path): nn.ZeroPad2d + the first Conv2d + bias + ReLU of
+ * Backbone (reference modules.py:12-111; layer 0 of config.py DEFAULT_BACKBONE_TOPOLOGY) in one
+ * launch each way.  HBM-bound (C*16 taps per output): the forward writes the [B,Cout,Ho,Wo] map once,
+ * the backward reads dy and the saved post-ReLU y once and produces d_w [Cout,C,4,4] and d_bias [Cout]
+ * (the image has no gradient).  Supported: C in {1,3}, Cout = 128, k = 4; padding is the ZeroPad2d's
+ * (top, left) — right / bottom padding is implied by Ho, Wo.  ws: workspace of
+ * spair_stem_bwd_ctas() * Cout * (C*16 + 4) floats, 16-byte aligned.
+ * ---------------------------------------------------------------------------------- */
+int spair_stem_bwd_ctas(void);
+int spair_stem_conv_fwd(const float* x, const float* w, const float* bias, int B, int C, int Ih, int Iw, int Cout,
+                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* y, void* stream);
+int spair_stem_conv_bwd(const float* x, const float* y, const float* dy, int B, int C, int Ih, int Iw, int Cout,
+                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* ws, float* d_w, float* d_bias,
+                        void* stream);
+
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
 

@@ -82,6 +82,9 @@ _SIGNATURES = {
     "spair_kl_fwd": [_P] * 6 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
+    "spair_stem_bwd_ctas": [],
+    "spair_stem_conv_fwd": [_P, _P, _P] + [_I] * 11 + [_P, _P],
+    "spair_stem_conv_bwd": [_P, _P, _P] + [_I] * 11 + [_P, _P, _P, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
@@ -129,7 +132,8 @@ def base_grid(n: int) -> torch.Tensor:
 
 
 # kernels launched per C-ABI call (render_bwd = prep + object kernel; paste_bwd's memset is not a kernel)
-_LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0, "spair_sweep_max_rows": 0}
+_LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0, "spair_sweep_max_rows": 0, "spair_stem_bwd_ctas": 0,
+                      "spair_stem_conv_bwd": 2}
 LAUNCH_COUNT = 0
 
 
@@ -272,6 +276,34 @@ def pres_head_bwd(y, u, cells, B, HW, wheel, d_local, d_img, d_y):
 def relu_bwd(dh, h):
     _check(lib().spair_relu_bwd(_ptr(dh), _ld(dh), _ptr(h), _ld(h), dh.shape[0], dh.shape[1], _stream()),
            "spair_relu_bwd")
+
+
+# ----------------------------------------------------------------------------------------
+# backbone stem: ZeroPad2d + Conv2d(C -> 128, 4x4, stride s) + bias + ReLU
+# ----------------------------------------------------------------------------------------
+def stem_supported(C: int, Cout: int, k) -> bool:
+    return C in (1, 3) and Cout == 128 and tuple(k) == (4, 4)
+
+
+def stem_conv_fwd(x, w, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int, y):
+    B, C, Ih, Iw = x.shape
+    for t in (x, w, bias, y):
+        _contig(t, "stem tensor")
+    _check(lib().spair_stem_conv_fwd(_ptr(x), _ptr(w), _ptr(bias), B, C, Ih, Iw, w.shape[0], w.shape[2], stride, pad_t, pad_l,
+                                     Ho, Wo, _ptr(y), _stream()), "spair_stem_conv_fwd")
+
+
+def stem_bwd_workspace(C: int, Cout: int, device) -> torch.Tensor:
+    return torch.empty(lib().spair_stem_bwd_ctas() * Cout * (C * 16 + 4), device=device, dtype=torch.float32)
+
+
+def stem_conv_bwd(x, y, dy, w_shape, stride: int, pad_t: int, pad_l: int, ws, d_w, d_bias):
+    B, C, Ih, Iw = x.shape
+    Ho, Wo = y.shape[2], y.shape[3]
+    for t in (x, y, dy, ws, d_w, d_bias):
+        _contig(t, "stem tensor")
+    _check(lib().spair_stem_conv_bwd(_ptr(x), _ptr(y), _ptr(dy), B, C, Ih, Iw, w_shape[0], w_shape[2], stride, pad_t, pad_l,
+                                     Ho, Wo, _ptr(ws), _ptr(d_w), _ptr(d_bias), _stream()), "spair_stem_conv_bwd")
 
 
 # ----------------------------------------------------------------------------------------

@@ -83,7 +83,32 @@ class Backbone(Module):
         with torch.no_grad():
             return self(probe.to(next(self.parameters()).device)).shape[1:]
 
+    def _fused_stem(self, x):
+        """ZeroPad2d + conv_0 + act_0 as one sm_100a kernel each way (csrc/stem.cu) when the layer has the shape the
+        kernel covers and the image needs no gradient; None otherwise (library path)."""
+        conv = self.net[0]
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and not x.requires_grad
+                and isinstance(conv, Conv2d) and isinstance(self.net[1], ReLU) and conv.bias is not None
+                and conv.padding == (0, 0) and conv.dilation == (1, 1) and conv.groups == 1
+                and conv.stride[0] == conv.stride[1] and conv.weight.dtype == torch.float32):
+            return None
+        from . import kernels as K, ops
+        if not K.stem_supported(conv.in_channels, conv.out_channels, conv.kernel_size) or x.shape[1] != conv.in_channels:
+            return None
+        pl, pr, pt, pb = self.padding.padding
+        stride, k = conv.stride[0], conv.kernel_size[0]
+        Ho = (x.shape[2] + pt + pb - k) // stride + 1
+        Wo = (x.shape[3] + pl + pr - k) // stride + 1
+        if Ho <= 0 or Wo <= 0:
+            return None
+        return ops.StemConvFunction.apply(x, conv.weight, conv.bias, stride, pt, pl, Ho, Wo)
+
     def forward(self, x):
+        y = self._fused_stem(x)
+        if y is not None:
+            for layer in list(self.net)[2:]:
+                y = layer(y)
+            return y
         return self.net(self.padding(x))
 
 

@@ -268,6 +268,32 @@ class _ManualMLP:
         return self.dW, self.db
 
 
+class StemConvFunction(torch.autograd.Function):
+    """relu(conv2d(zero_pad(x), weight, bias, stride)) for the first backbone layer (reference modules.py:44-66,86-87) as one
+    launch forward and one (+ a small fixed-order reduction) backward.  ``x`` gets no gradient (the model's image is a
+    leaf without grad; callers that need d_x keep the library path)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int):
+        x = x.contiguous()
+        w = weight.detach().contiguous()
+        y = torch.empty(x.shape[0], w.shape[0], Ho, Wo, device=x.device, dtype=torch.float32)
+        K.stem_conv_fwd(x, w, bias.detach().contiguous(), stride, pad_t, pad_l, Ho, Wo, y)
+        ctx.save_for_backward(x, y)
+        ctx.geom = (stride, pad_t, pad_l, tuple(w.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        stride, pad_t, pad_l, w_shape = ctx.geom
+        d_w = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+        d_b = torch.empty(w_shape[0], device=x.device, dtype=torch.float32)
+        ws = K.stem_bwd_workspace(x.shape[1], w_shape[0], x.device)
+        K.stem_conv_bwd(x, y, dy.contiguous(), w_shape, stride, pad_t, pad_l, ws, d_w, d_b)
+        return None, d_w, d_b, None, None, None, None, None
+
+
 class CellSweepFunction(torch.autograd.Function):
     """forward(plan, x, feat, edge, eps_where, eps_attr, eps_depth, u_pres, wheel, *params)
     -> (z_where [B,HW,4], attr [B,HW,A], depth [B,HW], pres [B,HW], dmean [B,HW,D], dstd [B,HW,D], box [B,HW,4])

@@ -412,3 +412,51 @@ def test_sweep_weight_packing_is_exact(shapes):
         wb = torch.zeros(4 * n4, k)
         wb[:n] = w
         assert torch.equal(b.cpu().view(n4, k, 4), wb.view(n4, 4, k).permute(0, 2, 1)), "backward layout"
+
+
+@pytest.mark.parametrize("B,C,I,stride,pad", [(3, 1, 128, 3, (9, 14, 9, 14)), (2, 3, 64, 2, (7, 7, 7, 7)), (2, 1, 37, 3, (2, 5, 1, 3)),
+                                              (5, 3, 41, 1, (0, 0, 0, 0))])
+def test_stem_conv_vs_torch_cpu(B, C, I, stride, pad):
+    """Backbone stem (ZeroPad2d + Conv2d(C,128,4,stride) + ReLU, reference modules.py:44-66,86-87): forward map and
+    weight / bias gradients against the same ops in torch fp32 on the CPU."""
+    from spair_pytorch_b200 import ops
+    rs = gen(11)
+    x = torch.rand(B, C, I, I, generator=rs)
+    w = (torch.randn(128, C, 4, 4, generator=rs) * 0.2).requires_grad_(True)
+    b = (torch.randn(128, generator=rs) * 0.1).requires_grad_(True)
+    want = torch.relu(torch.nn.functional.conv2d(torch.nn.functional.pad(x, pad), w, b, stride=stride))
+    cot = torch.randn(want.shape, generator=rs)
+    want.backward(cot)
+    wd, bd = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+    pl, pr, pt, pb = pad
+    got = ops.StemConvFunction.apply(x.to(DEV), wd, bd, stride, pt, pl, want.shape[2], want.shape[3])
+    got.backward(cot.to(DEV))
+    assert_close(got, want, "stem forward")
+    helpers.assert_close(wd.grad.cpu(), w.grad, "stem d_weight", atol=helpers.ATOL + helpers.RTOL * float(w.grad.norm()) / w.grad.numel() ** 0.5)
+    helpers.assert_close(bd.grad.cpu(), b.grad, "stem d_bias", atol=helpers.ATOL + helpers.RTOL * float(b.grad.norm()) / b.grad.numel() ** 0.5)
+
+
+def test_backbone_uses_fused_stem_and_matches_library_path():
+    """Backbone.forward routes layer 0 through the stem kernel on CUDA; same features and parameter gradients as the
+    cuDNN path of the same module (image with requires_grad takes the library path)."""
+    from spair_pytorch_b200 import kernels as kk
+    from spair_pytorch_b200.modules import Backbone
+    torch.backends.cudnn.allow_tf32 = False          # strict fp32 on the library path too (the model sets this itself)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(5)
+    net = Backbone([1, 128, 128], 100).to(DEV)
+    x = torch.rand(4, 1, 128, 128, device=DEV)
+    n0 = kk.launch_count()
+    y = net(x)
+    assert kk.launch_count() == n0 + 1, "fused stem not used"
+    y.square().sum().backward()
+    g_fused = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    xr = x.clone().requires_grad_(True)
+    n0 = kk.launch_count()
+    y_ref = net(xr)
+    assert kk.launch_count() == n0, "library path expected when the image needs a gradient"
+    y_ref.square().sum().backward()
+    assert_close(y, y_ref, "backbone features")
+    for (name, p), g in zip(net.named_parameters(), g_fused):
+        helpers.assert_close(g, p.grad, "backbone grad " + name, atol=helpers.ATOL + helpers.RTOL * float(p.grad.norm()) / p.grad.numel() ** 0.5)
