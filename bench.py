@@ -154,8 +154,27 @@ def kernel_roofline(net, x, steps=20):
     def t_glimpse_bwd():
         K.glimpse_bwd(x, L.z_where, cells, B, HW, G, G, d_gl, d_zw_l, None)
 
+    # backbone stem (ZeroPad2d + conv_0 + bias + ReLU; csrc/stem.cu) on the step's own batch
+    conv0 = net.backbone.net[0]
+    pl, pr, pt, pb = net.backbone.padding.padding
+    s0 = conv0.stride[0]
+    Ho, Wo = (I + pt + pb - 4) // s0 + 1, (I + pl + pr - 4) // s0 + 1
+    stem_y = torch.empty(B, conv0.out_channels, Ho, Wo, device=dev)
+    stem_dy = torch.randn_like(stem_y)
+    stem_ws = K.stem_bwd_workspace(C, conv0.out_channels, dev)
+    stem_dw, stem_db = torch.empty_like(conv0.weight), torch.empty_like(conv0.bias)
+    w0, b0 = conv0.weight.detach().contiguous(), conv0.bias.detach().contiguous()
+
+    def t_stem_fwd():
+        K.stem_conv_fwd(x, w0, b0, s0, pt, pl, Ho, Wo, stem_y)
+
+    def t_stem_bwd():
+        K.stem_conv_bwd(x, stem_y, stem_dy, tuple(w0.shape), s0, pt, pl, stem_ws, stem_dw, stem_db)
+
     # algorithmic bytes per image
     per_image = {
+        "stem_fwd": 4 * C * I * I + 4 * conv0.out_channels * Ho * Wo,
+        "stem_bwd": 4 * C * I * I + 8 * conv0.out_channels * Ho * Wo,
         "render_fwd": HW * (4 * (C + 1) * G * G + 24) + 4 * C * I * I,
         "render_bwd": 4 * C * I * I + HW * (8 * (C + 1) * G * G + 48),
         "glimpse_fwd": 4 * C * I * I + HW * (16 + 4 * C * G * G),
@@ -164,7 +183,7 @@ def kernel_roofline(net, x, steps=20):
     peak, peak_src = measured_hbm_peak()
     out = {}
     for name, fn in (("render_fwd", t_render_fwd), ("render_bwd", t_render_bwd), ("glimpse_fwd", t_glimpse_fwd),
-                     ("glimpse_bwd", t_glimpse_bwd)):
+                     ("glimpse_bwd", t_glimpse_bwd), ("stem_fwd", t_stem_fwd), ("stem_bwd", t_stem_bwd)):
         for _ in range(3):
             fn()
         times = []
@@ -180,7 +199,8 @@ def kernel_roofline(net, x, steps=20):
         nbytes = per_image[name] * B
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "bytes": nbytes, "achieved": gbs, "frac": gbs / peak}
-    dom = max(out, key=lambda k: out[k]["ms"])       # dominant of the glimpse / render kernels BASELINE's metric names
+    # dominant of the glimpse / render kernels BASELINE's metric names (the stem kernels are the caller side of the path)
+    dom = max((k for k in out if not k.startswith("stem")), key=lambda k: out[k]["ms"])
     # the fused cell sweep: ONE persistent launch per direction holding all 31 wavefronts x 4 three-layer MLPs (fp32 SIMT
     # dot products on <= 16 rows per CTA: latency / issue bound, not HBM work) — reported with its FLOP rate next to
     # the HBM-bound kernels.  Timed with CUDA events placed directly around the two launches inside the operator.
