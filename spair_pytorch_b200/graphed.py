@@ -25,6 +25,7 @@ class GraphedTrainStep:
         if not example_x.is_cuda:
             raise ValueError("GraphedTrainStep needs a CUDA batch")
         self.net = net
+        self._copy_stream, self._staged, self._staged_ready, self._staged_free, self._has_staged = None, None, None, None, False
         self.bucket = bucket if bucket is not None else GradientBucket(trainable_parameters(net))
         self.static_x = example_x.detach().clone().float().contiguous()
         dev = example_x.device
@@ -52,10 +53,38 @@ class GraphedTrainStep:
             net._static_step = False
         self.bucket.check_attached()
 
-    def __call__(self, x: torch.Tensor, global_step: int):
-        """Runs one captured step on ``x`` (device tensor, or pinned host tensor — copied asynchronously).
-        Returns the static output tuple (loss, recon_x, z_where, z_pres); gradients are in the bucket."""
-        self.net.prepare_step(global_step, self.static_x.device)
-        self.static_x.copy_(x, non_blocking=True)
+    def prefetch(self, x_host: torch.Tensor) -> None:
+        """Starts the host->device copy of the NEXT step's batch on a copy stream, so that it overlaps the step that is
+        running (input double buffering: the captured graph reads ``static_x``, the copy lands in a second buffer).
+        The next ``__call__(None, step)`` consumes it.  ``x_host`` should be pinned."""
+        dev = self.static_x.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = torch.empty_like(self.static_x)
+            self._staged_ready = torch.cuda.Event()
+            self._staged_free = torch.cuda.Event()
+            self._staged_free.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._staged_free)          # the previous consumer of the staging buffer is done
+        with torch.cuda.stream(self._copy_stream):
+            self._staged.copy_(x_host, non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._has_staged = True
+
+    def __call__(self, x, global_step: int):
+        """Runs one captured step on ``x`` (device tensor, or pinned host tensor — copied asynchronously; ``None`` = the
+        batch staged by ``prefetch``).  Returns the static output tuple (loss, recon_x, z_where, z_pres); gradients are
+        in the bucket."""
+        dev = self.static_x.device
+        self.net.prepare_step(global_step, dev)
+        if x is None:
+            if not self._has_staged:
+                raise RuntimeError("no batch staged: call prefetch(x_host) first")
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(self._staged_ready)
+            self.static_x.copy_(self._staged, non_blocking=True)
+            self._staged_free.record(cur)
+            self._has_staged = False
+        else:
+            self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.out

@@ -166,6 +166,17 @@ def test_graphed_step_equals_eager_step():
         torch.cuda.synchronize()
         assert torch.equal(loss, loss_w)
         assert torch.equal(bucket.flat, grad_w)
+    # input double buffering: a pinned host batch staged on the copy stream, consumed by the next replay
+    gstep.prefetch(xs[0].cpu().pin_memory())
+    loss = gstep(None, 1200)[0]
+    gstep.prefetch(xs[1].cpu().pin_memory())        # staged while the step above may still be running
+    torch.cuda.synchronize()
+    assert torch.equal(loss, want[0][0]) and torch.equal(bucket.flat, want[0][1])
+    loss = gstep(None, 3000)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(loss, want[1][0]) and torch.equal(bucket.flat, want[1][1])
+    with pytest.raises(RuntimeError):
+        gstep(None, 1200)                            # nothing staged
     torch.backends.cudnn.deterministic = False
 
 
