@@ -38,7 +38,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("SPAIR_NVCC_EXTRA", "").split()      # e.g. -DSW_TIMING for tools/sweep_phase_timing.py
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -5,7 +5,7 @@
 // them with block-level barriers only — no kernel boundary, no grid-wide synchronisation.  Per wavefront a CTA
 // handles R = n_cells * ipc <= 16 rows through context gather -> box MLP -> box head -> glimpse -> encoder MLP ->
 // attr head -> z MLP -> depth head -> obj MLP -> presence head.  The MLP layers are register-tiled SIMT dot
-// products: a thread owns one output column, up to 16 rows and a slice of the reduction index; it streams PACKED
+// products: a thread owns two output columns, up to 16 rows and a slice of the reduction index; it streams PACKED
 // weights (four consecutive reduction indices of one column = one float4, spair_sweep_pack_weights) from L2 with
 // coalesced 128-bit loads and reads the activations as 128-bit shared-memory broadcasts; each weight element is
 // fetched once per CTA and wavefront and reused for all rows.  All activations are also written to the same
