@@ -223,7 +223,9 @@ class SPAIR(nn.Module):
             plan, x, feat, self.virtual_edge_element, *noise, wheel, *self._sweep_params())
 
         # decoder MLP over all N = B*HW objects at once (reference models.py:474-481), cuBLAS
-        logits = self.object_decoder(attr.reshape(B * HW, c.n_attr))
+        dec = self.object_decoder
+        hidden = dec[:-1](attr.reshape(B * HW, c.n_attr))
+        logits = ops.WideLinearFunction.apply(hidden, dec[-1].weight, dec[-1].bias)
         recon_x, recon_loss, _ = ops.RenderFunction.apply(logits, z_where.reshape(B * HW, 4), depth.reshape(-1),
                                                           pres.reshape(-1), x, B, HW, C, plan.G, Ih, Iw, c.scales)
         kl_sums, kl_map = ops.KLFunction.apply(dmean, dstd, pres, plan.prior_mean, plan.prior_std, count_dist0, c.n_attr)

@@ -268,6 +268,26 @@ class _ManualMLP:
         return self.dW, self.db
 
 
+class WideLinearFunction(torch.autograd.Function):
+    """``F.linear(h, weight, bias)`` for the decoder's output layer (reference models.py:165,477: 256 -> G*G*(C+1), a
+    [B*HW, 1568] result of 194 MB at the default config).  cuBLASLt applies the bias of an fp32 SIMT GEMM in a separate
+    un-fused pass over the output (0.22 ms); here the output is pre-filled with the bias rows and the GEMM accumulates
+    into it (beta = 1), which costs one 194 MB fill instead.  Same values as addmm up to the position of one rounding."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        out = bias.detach().unsqueeze(0).expand(h.shape[0], -1).contiguous()
+        torch.addmm(out, h, weight.detach().t(), out=out)
+        ctx.save_for_backward(h, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h, weight = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        return d_out.mm(weight), d_out.t().mm(h), d_out.sum(0)
+
+
 class StemConvFunction(torch.autograd.Function):
     """relu(conv2d(zero_pad(x), weight, bias, stride)) for the first backbone layer (reference modules.py:44-66,86-87) as one
     launch forward and one (+ a small fixed-order reduction) backward.  ``x`` gets no gradient (the model's image is a
