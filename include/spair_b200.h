@@ -340,6 +340,10 @@ int spair_stem_conv_bwd(const float* x, const float* y, const float* dy, int B, 
                         int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* ws, float* d_w, float* d_bias,
                         void* stream);
 
+/* out[r][:] = row[:] for r < rows (vectorised when cols % 4 == 0): pre-fills the decoder's [B*HW, G*G*(C+1)] logits
+ * (reference models.py:165,477) with the bias so that the output GEMM runs with beta = 1. */
+int spair_broadcast_rows(const float* row, int rows, int cols, float* out, void* stream);
+
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
 

@@ -97,7 +97,7 @@ struct StemBwdArgs {
     const float* x;      // [B,C,Ih,Iw]
     const float* y;      // [B,Cout,Ho,Wo] saved post-ReLU output
     const float* dy;     // [B,Cout,Ho,Wo]
-    float* ws;           // [gridDim.x, Cout, TP] per-CTA partial sums
+    float* ws;           // [Cout * TP][gridDim.x] per-CTA partial sums (CTA index fastest: the reduction reads rows)
     int B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l, n_seg_per_image;
     int vec_ok;          // rows of y / dy are 16-byte aligned: 128-bit staging loads
 };
@@ -190,23 +190,42 @@ __global__ void __launch_bounds__(32 * (C * 16 + 4) / 4) stem_bwd_kernel(StemBwd
             }
         }
     }
-    float* wsb = p.ws + (size_t)blockIdx.x * kStemCout * TP;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(wsb + (size_t)(og + 32 * i) * TP + 4 * tg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p.ws[(size_t)((og + 32 * i) * TP + 4 * tg + k) * gridDim.x + blockIdx.x] = acc[i][k];
 }
 
-// dW[o][t] = sum over CTAs of ws[cta][o][t] (t < T), db[o] = sum of ws[cta][o][T]; fixed order
+// dW[o][t] = sum over CTAs of ws[o*TP + t][cta] (t < T), db[o] = sum of ws[o*TP + T][cta]: one warp per output, lanes
+// stride over the CTAs, butterfly at the end — a fixed order, so the result is reproducible
 __global__ void __launch_bounds__(256) stem_bwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int T, int TP,
                                                              float* __restrict__ dW, float* __restrict__ db) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (idx >= kStemCout * TP) return;
     const int o = idx / TP, t = idx - o * TP;
     if (t > T) return;
     float s = 0.0f;
-    for (int c = 0; c < n_cta; ++c) s += ws[(size_t)c * kStemCout * TP + idx];
-    if (t < T) dW[o * T + t] = s;
-    else db[o] = s;
+    for (int c = lane; c < n_cta; c += 32) s += ws[(size_t)idx * n_cta + c];
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (t < T) dW[o * T + t] = s;
+        else db[o] = s;
+    }
+}
+
+// out[r][:] = row[:] for all r: the bias rows a beta = 1 GEMM then accumulates into (ops.WideLinearFunction)
+__global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __restrict__ row, int rows, int cols, float* __restrict__ out) {
+    const size_t total = (size_t)rows * cols;
+    if ((cols & 3) == 0) {
+        const int c4 = cols >> 2;
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (size_t)gridDim.x * blockDim.x)
+            o4[i] = __ldg(r4 + (int)(i % c4));
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+            out[i] = __ldg(row + (int)(i % cols));
+    }
 }
 
 }  // namespace spair
@@ -249,6 +268,13 @@ extern "C" int spair_stem_conv_bwd(const float* x, const float* y, const float* 
     const int T = C * 16, TP = T + 4;
     if (C == 1) stem_bwd_kernel<1><<<n_cta, 32 * (16 + 4) / 4, 0, (cudaStream_t)stream>>>(a);
     else stem_bwd_kernel<3><<<n_cta, 32 * (48 + 4) / 4, 0, (cudaStream_t)stream>>>(a);
-    stem_bwd_reduce_kernel<<<(kStemCout * TP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, n_cta, T, TP, d_w, d_bias);
+    stem_bwd_reduce_kernel<<<(kStemCout * TP + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ws, n_cta, T, TP, d_w, d_bias);
+    SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_broadcast_rows(const float* row, int rows, int cols, float* out, void* stream) {
+    SPAIR_REQUIRE(row && out && rows > 0 && cols > 0);
+    SPAIR_REQUIRE((cols % 4) != 0 || (((uintptr_t)row % 16) == 0 && ((uintptr_t)out % 16) == 0));
+    broadcast_rows_kernel<<<kSMs * 8, 256, 0, (cudaStream_t)stream>>>(row, rows, cols, out);
     SPAIR_LAUNCH_CHECK();
 }

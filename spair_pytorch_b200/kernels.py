@@ -85,6 +85,7 @@ _SIGNATURES = {
     "spair_stem_bwd_ctas": [],
     "spair_stem_conv_fwd": [_P, _P, _P] + [_I] * 11 + [_P, _P],
     "spair_stem_conv_bwd": [_P, _P, _P] + [_I] * 11 + [_P, _P, _P, _P],
+    "spair_broadcast_rows": [_P, _I, _I, _P, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
@@ -291,6 +292,11 @@ def stem_conv_fwd(x, w, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: 
         _contig(t, "stem tensor")
     _check(lib().spair_stem_conv_fwd(_ptr(x), _ptr(w), _ptr(bias), B, C, Ih, Iw, w.shape[0], w.shape[2], stride, pad_t, pad_l,
                                      Ho, Wo, _ptr(y), _stream()), "spair_stem_conv_fwd")
+
+
+def broadcast_rows(row, rows: int, out):
+    _check(lib().spair_broadcast_rows(_ptr(_contig(row, "row")), rows, row.numel(), _ptr(_contig(out, "out")), _stream()),
+           "spair_broadcast_rows")
 
 
 def stem_bwd_workspace(C: int, Cout: int, device) -> torch.Tensor:

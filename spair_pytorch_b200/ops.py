@@ -276,7 +276,8 @@ class WideLinearFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, weight, bias):
-        out = bias.detach().unsqueeze(0).expand(h.shape[0], -1).contiguous()
+        out = torch.empty(h.shape[0], weight.shape[0], device=h.device, dtype=torch.float32)
+        K.broadcast_rows(bias.detach().contiguous(), h.shape[0], out)
         torch.addmm(out, h, weight.detach().t(), out=out)
         ctx.save_for_backward(h, weight)
         return out

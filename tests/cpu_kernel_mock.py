@@ -197,6 +197,10 @@ def relu_bwd(dh, h):
     dh.mul_((h > 0).float())
 
 
+def broadcast_rows(row, rows, out):
+    out.copy_(row.unsqueeze(0).expand(rows, -1))
+
+
 # ------------------------------------------------------------------------------------------
 def glimpse_fwd(image, z_where, cells, B, HW, Gh, Gw, out):
     if cells is None:
