@@ -147,46 +147,50 @@ __device__ __forceinline__ void store_partials(const float (&a)[NR], const float
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Issued BEFORE the accumulation: pulls the bias / ReLU-mask words finalize_columns will read into L1, so that their
-// L2 / HBM latency overlaps the weight stream instead of following it.
-template <int NCOLP>
-__device__ __forceinline__ void prefetch_epilogue(const float* __restrict__ bias, const float* __restrict__ Hmask,
-                                                  int ncols_total, int c0, int nrows, const int* __restrict__ grow) {
-    if (bias && threadIdx.x * 32 < NCOLP && c0 + threadIdx.x * 32 < ncols_total) prefetch_l1(bias + c0 + threadIdx.x * 32);
-    if (Hmask) {
-        constexpr int kLines = NCOLP / 32;                      // 128-byte lines per row and pass
-        for (int idx = threadIdx.x; idx < nrows * kLines; idx += kSwThreads) {
-            const int r = idx / kLines, col = c0 + (idx % kLines) * 32;
-            if (col < ncols_total) prefetch_l1(Hmask + (size_t)grow[r] * ncols_total + col);
+// Epilogue of one pass over NCOLP columns.  A thread finalises column n = tid % NCOLP for the rows r0, r0 + RS, ...
+// (r0 = tid / NCOLP, RS = 512 / NCOLP).  Its bias word and the ReLU-mask words of its rows are loaded BEFORE the
+// accumulation (`preload`), so their L2 / HBM latency overlaps the weight stream instead of following the barrier.
+template <int NR, int NCOLP>
+struct Epilogue {
+    static constexpr int RS = kSwThreads / NCOLP;          // row stride of a thread: 4 or 2
+    static constexpr int NV = (NR + RS - 1) / RS;          // rows per thread
+    float bias;
+    float mask[NV];
+
+    __device__ __forceinline__ void preload(const float* __restrict__ b, const float* __restrict__ Hmask, int ncols_total,
+                                            int c0, int nrows, const int* __restrict__ grow) {
+        const int col = c0 + threadIdx.x % NCOLP, r0 = threadIdx.x / NCOLP;
+        const bool colv = col < ncols_total;
+        bias = (b && colv) ? __ldg(b + col) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int r = r0 + j * RS;
+            mask[j] = (Hmask && colv && r < nrows) ? Hmask[(size_t)grow[r] * ncols_total + col] : 1.0f;
         }
     }
-}
 
-// out[r][c0 + n] = act(bias + sum over K-slices); rows >= nr_comp are zero
-template <int NCOLP>
-__device__ __forceinline__ void finalize_columns(const float* part, const float* __restrict__ bias, int ncols_total, int c0,
-                                                 int nr_comp, int nrows, bool relu, const float* __restrict__ Hmask,
-                                                 const int* __restrict__ grow, float* out_smem, float* __restrict__ out_glob,
-                                                 int ld_out) {
-    constexpr int KS = SliceMap<NCOLP>::KS;
-    for (int idx = threadIdx.x; idx < kSwRows * NCOLP; idx += kSwThreads) {
-        const int r = idx / NCOLP, n = idx % NCOLP, col = c0 + n;
-        if (col >= ncols_total) continue;
-        float v = 0.0f;
-        if (r < nr_comp) {
-            v = bias ? __ldg(bias + col) : 0.0f;
+    // out[r][c0 + n] = act(bias + sum over the K-slices) (* mask); rows in [nrows, NR) are written as zero to shared memory
+    __device__ __forceinline__ void finalize(const float* part, int ncols_total, int c0, int nrows, bool relu,
+                                             const int* __restrict__ grow, float* out_smem, float* __restrict__ out_glob,
+                                             int ld_out) const {
+        constexpr int KS = SliceMap<NCOLP>::KS;
+        const int n = threadIdx.x % NCOLP, col = c0 + n, r0 = threadIdx.x / NCOLP;
+        if (col >= ncols_total) return;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int r = r0 + j * RS;
+            if (r >= NR) break;
+            float v = bias;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) v += part[(ks * kSwRows + r) * NCOLP + n];
             if (relu) v = fmaxf(v, 0.0f);
+            if (!(mask[j] > 0.0f)) v = 0.0f;
+            if (r < nrows) out_glob[(size_t)grow[r] * ld_out + col] = v;
+            else v = 0.0f;
+            if (out_smem) out_smem[r * kSwHP + col] = v;
         }
-        if (r < nrows) {
-            const size_t g = grow[r];
-            if (Hmask && !(Hmask[g * ncols_total + col] > 0.0f)) v = 0.0f;
-            out_glob[g * ld_out + col] = v;
-        }
-        if (out_smem) out_smem[r * kSwHP + col] = v;
     }
-}
+};
 
 // forward layer: out = act(in . W^T + b).  in_smem != nullptr: activations in shared memory [r][kSwHP]; otherwise the
 // input rows live in global memory (Xg) and are staged through `chunk` in slabs of kSwKC columns.
@@ -195,7 +199,8 @@ __device__ __noinline__ void dense_layer_t(const SweepLayer L, const float* in_s
                               const int* __restrict__ grow, int nrows, float* chunk, float* part, float* out_smem,
                               float* __restrict__ out_glob, bool relu) {
     SW_T0();
-    prefetch_epilogue<NCOLP>(L.b, nullptr, L.N, 0, nrows, grow);
+    Epilogue<NR, NCOLP> epi;
+    epi.preload(L.b, nullptr, L.N, 0, nrows, grow);
     float a[NR], b[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0f;
@@ -220,7 +225,7 @@ __device__ __noinline__ void dense_layer_t(const SweepLayer L, const float* in_s
     store_partials<NR, NCOLP>(a, b, part);
     __syncthreads();
     SW_MARK(21);
-    finalize_columns<NCOLP>(part, L.b, L.N, 0, NR, nrows, relu, nullptr, grow, out_smem, out_glob, L.N);
+    epi.finalize(part, L.N, 0, nrows, relu, grow, out_smem, out_glob, L.N);
     __syncthreads();
     SW_MARK(22);
 }
@@ -493,7 +498,8 @@ __device__ __noinline__ void dense_bwd_layer_t(const float4* __restrict__ W, int
     const int ng = (Nred + 3) >> 2;
     for (int c0 = 0; c0 < Kout; c0 += NCOLP) {
         SW_T0();
-        prefetch_epilogue<NCOLP>(nullptr, Hmask, Kout, c0, nrows, grow);
+        Epilogue<NR, NCOLP> epi;
+        epi.preload(nullptr, Hmask, Kout, c0, nrows, grow);
         float a[NR], b[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0f;
@@ -502,7 +508,7 @@ __device__ __noinline__ void dense_bwd_layer_t(const float4* __restrict__ W, int
         store_partials<NR, NCOLP>(a, b, part);
         __syncthreads();
         SW_MARK(41);
-        finalize_columns<NCOLP>(part, nullptr, Kout, c0, NR, nrows, false, Hmask, grow, out_smem, out_glob, ld_out);
+        epi.finalize(part, Kout, c0, nrows, false, grow, out_smem, out_glob, ld_out);
         __syncthreads();
         SW_MARK(42);
     }
