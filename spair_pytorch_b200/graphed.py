@@ -41,11 +41,15 @@ class GraphedTrainStep:
                 net(self.static_x, global_step)[0].backward()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the warm-up graphs go too: the capture then creates its own AccumulateGrad nodes on the capture stream (the same
+        # side stream), so the captured backward needs no cross-stream hand-over for the parameter gradients
+        net._latents, net.dist_param, net.dist = None, {}, {}
+        gc.collect()
         net.prepare_step(global_step, dev)
         self.graph = torch.cuda.CUDAGraph()
         net._static_step = True
         try:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self.bucket.zero()
                 self.out = net(self.static_x, global_step)
                 self.out[0].backward()
