@@ -145,8 +145,6 @@ __device__ __forceinline__ void store_partials(const float (&a)[NR], const float
     }
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // Epilogue of one pass over NCOLP columns.  A thread finalises column n = tid % NCOLP for the rows r0, r0 + RS, ...
 // (r0 = tid / NCOLP, RS = 512 / NCOLP).  Its bias word and the ReLU-mask words of its rows are loaded BEFORE the
 // accumulation (`preload`), so their L2 / HBM latency overlaps the weight stream instead of following the barrier.
