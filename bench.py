@@ -277,7 +277,7 @@ def run_ours(args):
     net = helpers.build_model(CONFIG_NAME, dev)
     ddp = dp.DataParallelSPAIR(net, world_size=world)
     ddp.broadcast_parameters()
-    opt = torch.optim.Adam([p for _, p in dp.trainable_parameters(net)], lr=1e-4, fused=True)
+    opt = torch.optim.Adam([ddp.bucket.flatten_parameters()], lr=1e-4, fused=True)   # one kernel over the flat parameters
     B = args.batch
     image_shape = tuple(net.image_shape)
     host_batches = make_batches(4, B, image_shape, seed=1234 + rank)

@@ -52,7 +52,8 @@ def _bucket_worker(rank, world, port, q):
     torch.manual_seed(0)
     m = Toy()
     bucket = dp.GradientBucket(dp.trainable_parameters(m))
-    assert bucket.flat.numel() == 15 + 3 + 4 and m.attn.weight.grad is None
+    assert bucket.flat.numel() == 3 * dp.GradientBucket.ALIGN and bucket.offsets == [0, 64, 128]   # 4, 15, 3 elements, padded
+    assert m.attn.weight.grad is None
     x = torch.arange(10.0).view(2, 5) + rank
     (m.a(x).sum() * (rank + 1) + (m.b * (rank + 2)).sum()).backward()
     assert [n for n, _ in bucket.params] == ["b", "a.weight", "a.bias"]
@@ -104,9 +105,11 @@ def test_gradient_bucket_allreduce_world2():
     # d/dW of sum(Linear(x)) * k summed over ranks: rows equal to sum_r (r+1) * sum_b x_r[b]
     x0, x1 = torch.arange(10.0).view(2, 5), torch.arange(10.0).view(2, 5) + 1
     want_row = 1 * x0.sum(0) + 2 * x1.sum(0)
+    # tensors start on 64-float boundaries (GradientBucket.ALIGN); the padding stays zero through the allreduce
     assert torch.allclose(g0[:4], torch.full((4,), 2.0 + 3.0))
-    assert torch.allclose(g0[4:19].view(3, 5), want_row.expand(3, 5))
-    assert torch.allclose(g0[19:], torch.full((3,), 2.0 * 1 + 2.0 * 2))
+    assert torch.allclose(g0[64:79].view(3, 5), want_row.expand(3, 5))
+    assert torch.allclose(g0[128:131], torch.full((3,), 2.0 * 1 + 2.0 * 2))
+    assert not g0[4:64].any() and not g0[79:128].any() and not g0[131:].any()
 
 
 def test_spair_data_parallel_equals_single_process(monkeypatch):

@@ -29,3 +29,31 @@ def test_product_path_refuses_cpu_tensors():
     net = helpers.build_model("tiny")
     with pytest.raises(K.SpairKernelError):
         net(torch.zeros(2, 1, 40, 40), 1)
+
+
+def test_flat_parameter_adam_equals_per_tensor_adam():
+    """dp.GradientBucket.flatten_parameters: parameters aliased into one flat buffer, Adam over the single flat Parameter
+    (grad = the gradient bucket) performs exactly the per-tensor updates."""
+    import copy
+    from spair_pytorch_b200 import dp
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Conv2d(2, 3, 3), torch.nn.Flatten(), torch.nn.Linear(3 * 6 * 6, 5))
+    net = copy.deepcopy(ref)
+    bucket = dp.GradientBucket(list(net.named_parameters()))
+    flat = bucket.flatten_parameters()
+    assert flat.grad is bucket.flat and bucket.flatten_parameters() is flat
+    for (_, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert torch.equal(p, q) and p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4
+    opt_flat = torch.optim.Adam([flat], lr=1e-2, foreach=False)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, foreach=False)
+    for it in range(4):
+        x = torch.randn(7, 2, 8, 8)
+        bucket.zero()
+        net(x).square().sum().backward()
+        bucket.check_attached()
+        opt_flat.step()
+        opt_ref.zero_grad()
+        ref(x).square().sum().backward()
+        opt_ref.step()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            assert torch.equal(p, q), "update %d differs" % it

@@ -80,7 +80,7 @@ def main():
     net = SPAIR(cfg.INPUT_IMAGE_SHAPE, writer if args.eager else _NullWriter(), dev).to(dev)
     ddp = dp.DataParallelSPAIR(net, world_size=world)
     ddp.broadcast_parameters()
-    opt = torch.optim.Adam([p for _, p in dp.trainable_parameters(net)], lr=args.lr, fused=True)   # train.py:44
+    opt = torch.optim.Adam([ddp.bucket.flatten_parameters()], lr=args.lr, fused=True)   # train.py:44, over the flat buffer
     step = args.start_step
     if args.resume and args.ckpt_dir and newest_checkpoint(args.ckpt_dir):
         ck = torch.load(newest_checkpoint(args.ckpt_dir), map_location=dev)
