@@ -17,6 +17,8 @@ CONFIG_OVERRIDES = {
     "C": dict(OBJECT_SHAPE=[14, 14], topology="cell8"),
     "D": dict(INPUT_IMAGE_SHAPE=[3, 256, 256], topology="cell8"),
     "rgb64": dict(INPUT_IMAGE_SHAPE=[3, 64, 64], OBJECT_SHAPE=[14, 14], topology="cell8"),
+    # lateral context of radius 2: 12 neighbours, wavefronts t = w + 3h (reference models.py:26,292-320 with N_LOOKBACK = 2)
+    "tiny_lb2": dict(INPUT_IMAGE_SHAPE=[1, 40, 40], OBJECT_SHAPE=[8, 8], ANCHORBOX_SHAPE=[16, 16], topology="cell8", N_LOOKBACK=2),
 }
 
 
@@ -57,7 +59,9 @@ def build_model(name, device="cpu", seed=3):
 
 def oracle_config(name):
     from oracle import spair_oracle as so
+    import dataclasses
     return dict(A=so.config_A, tiny=so.config_tiny, C=so.config_C, D=so.config_D,
+                tiny_lb2=lambda: dataclasses.replace(so.config_tiny(), n_lookback=2),
                 rgb64=lambda: so.OracleConfig(image_shape=(3, 64, 64), object_shape=(14, 14),
                                               topology=copy.deepcopy(so.CELL8_TOPOLOGY)))[name]()
 

@@ -24,6 +24,30 @@ def test_model_orchestration_matches_reference_golden_A(monkeypatch):
     helpers.check_model_against_golden(net, g, "cpu")
 
 
+def test_model_orchestration_lookback2_matches_oracle(monkeypatch):
+    """N_LOOKBACK = 2 (12 context neighbours, wavefronts t = w + 3h; reference models.py:26,292-320): schedule, context
+    gather / gradient gather and the hand-written backward against the oracle on the same inputs and noise."""
+    from oracle import spair_oracle as so
+    cpu_kernel_mock.install(monkeypatch)
+    net = helpers.build_model("tiny_lb2")
+    cfg = helpers.oracle_config("tiny_lb2")
+    x = so.scattered_sprites(3, cfg.image_shape, seed=11, sprite_px=(6, 14))
+    noise = so.random_noise(torch.Generator().manual_seed(5), 3, cfg.grid, cfg.n_attr)
+    params = so.params_from_state_dict(net.state_dict())
+    want = so.forward_backward(params, x, 1001, noise, cfg, check_finite=False)      # fills params[k].grad
+    net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)
+    loss, recon, z_where, z_pres = net(x, 1001)
+    loss.backward()
+    helpers.assert_close(loss, want["loss"], "loss")
+    helpers.assert_close(recon, want["recon_x"], "recon_x")
+    helpers.assert_close(z_where, want["z_where"], "z_where")
+    helpers.assert_close(z_pres, want["z_pres"], "z_pres")
+    for k, p in net.named_parameters():
+        if not k.startswith("attn."):
+            ref = params[k].grad
+            helpers.assert_close(p.grad, ref, "grad " + k, atol=1e-5 + 1e-4 * float(ref.norm()) / np.sqrt(ref.numel()))
+
+
 def test_product_path_refuses_cpu_tensors():
     from spair_pytorch_b200 import kernels as K
     net = helpers.build_model("tiny")

@@ -33,9 +33,9 @@ def _run_oracle(net, x, step, noise, name):
     return out, params
 
 
-@pytest.mark.parametrize("name,B,step", [("C", 2, 1001), ("rgb64", 2, 1001), ("A", 3, 2500), ("D", 1, 1001)])
+@pytest.mark.parametrize("name,B,step", [("C", 2, 1001), ("rgb64", 2, 1001), ("A", 3, 2500), ("D", 1, 1001), ("tiny_lb2", 3, 1001)])
 def test_model_vs_oracle_other_shapes(name, B, step):
-    """16x16 cells / 14x14 glimpses (config C), RGB with 8x8 cells, a later training step, and one image of
+    """16x16 cells / 14x14 glimpses (config C), RGB with 8x8 cells, a later training step, a lookback-2 context, and one image of
     BASELINE config 4 (256x256 RGB, 32x32 = 1024 cells, 28x28 glimpses; the oracle materialises 7.8 GB for it),
     checked against the oracle executed on the host in the same test."""
     from oracle import spair_oracle as so
