@@ -26,7 +26,7 @@ extern "C" {
 
 #define SPAIR_ERR_INVALID (-1)
 #define SPAIR_MAX_NEIGHBOURS 12
-#define SPAIR_ABI_VERSION 1
+#define SPAIR_ABI_VERSION 2   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows */
 
 int spair_abi_version(void);
 

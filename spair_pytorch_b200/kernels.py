@@ -94,6 +94,9 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
+ABI_VERSION = 2       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
+
+
 def lib() -> ctypes.CDLL:
     """Loads (building first if stale or missing) the kernel library.  Raises if unavailable."""
     global _LIB
@@ -112,8 +115,9 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(handle, name)
                     fn.argtypes = argtypes
                     fn.restype = ctypes.c_int
-                if handle.spair_abi_version() != 1:
-                    raise SpairKernelError("libspair_b200.so ABI version mismatch")
+                if handle.spair_abi_version() != ABI_VERSION:
+                    raise SpairKernelError("libspair_b200.so ABI version %d, binding expects %d: rebuild with "
+                                           "`python __graft_entry__.py`" % (handle.spair_abi_version(), ABI_VERSION))
                 _LIB = handle
     return _LIB
 
