@@ -178,7 +178,9 @@ def test_library_exports_every_declared_symbol_and_binding_matches_header():
         assert hasattr(handle, name), "missing export " + name
         assert K._SIGNATURES[name] == kinds, "binding of %s disagrees with the header" % name
     assert set(K._SIGNATURES) == set(declared)
-    assert handle.spair_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "spair_b200.h")).read()
+    header_version = int(re.search(r"#define\s+SPAIR_ABI_VERSION\s+(\d+)", header).group(1))
+    assert handle.spair_abi_version() == header_version == K.ABI_VERSION
 
 
 def test_base_grid_matches_torch_affine_grid_bit_exactly():
