@@ -242,7 +242,10 @@ def kernel_roofline(net, x, steps=20):
             "traffic_source": "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)" if traffic else None,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": out[dom]["bytes"], "ms_per_launch": out[dom]["ms"],
-            "timing": "CUDA events on the launching stream, 256 MB L2 flush between launches, mean of %d" % steps}
+            "timing": "CUDA events on the launching stream, 256 MB L2 flush between launches, mean of %d" % steps,
+            "note": "dominant kernel of the HBM-bound class BASELINE's metric names (glimpse / render); the two persistent sweep "
+                    "kernels are larger by time but are fp32 SIMT dot-product chains, reported under kernels.sweep_fwd / "
+                    "kernels.sweep_bwd against the fp32 FMA peak; stem_fwd / stem_bwd are the caller-side HBM kernels"}
     return roof, out
 
 
