@@ -5,7 +5,9 @@ This file is part of ``oracle/``: it is never imported by the product package
 ``/root/reference`` is mounted, the restatement in ``oracle/spair_oracle.py`` can be
 pinned against the real reference and golden vectors can be generated
 (``tests/golden/make_golden.py``).  ``/root/reference`` does not exist on the GPU box, so
-nothing that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may call this.
+nothing that runs there may read that path; what does travel is ``baseline/_ref/`` (a byte-for-byte copy made by
+``baseline/install_reference.py``, git-ignored), which ``bench.py``'s CPU legs and ``tests/test_train_py.py`` load
+through this module.
 
 What it does:
   * injects stub modules for ``tensorboardX``, ``matplotlib[.pyplot|.gridspec|.patches|
@@ -30,7 +32,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SPAIR_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# where the unmodified reference lives: the read-only mount of the build container, else the byte-for-byte copy that
+# baseline/install_reference.py places in the git-ignored baseline/_ref/ (which gpurun ships to the GPU box)
+_CANDIDATES = [os.environ.get("SPAIR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "spair", "models.py"))), "/root/reference")
 
 # stride-2/2/2 topology used by BASELINE.json configs 3 and 4 (cfg C/D)
 TOPOLOGY_CELL8 = [

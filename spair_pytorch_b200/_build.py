@@ -16,8 +16,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libspair_b200.so")
 SOURCES = ["heads.cu", "glimpse.cu", "render.cu", "kl.cu", "sweep.cu", "stem.cu"]
 HEADERS = ["common.cuh", "warp_math.cuh", os.path.join("..", "..", "include", "spair_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "shared"]
 
 
 def _nvcc() -> str:
@@ -36,17 +36,38 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles every csrc/*.cu to an object (one nvcc process per source, in parallel), then links the shared library.
+    Objects whose source and headers are older than the object are reused unless ``force``."""
     if not force and not is_stale():
         return LIB_PATH
     extra = os.environ.get("SPAIR_NVCC_EXTRA", "").split()      # e.g. -DSW_TIMING for tools/sweep_phase_timing.py
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_time = max(hdr_time, os.path.getmtime(os.path.abspath(__file__)))
+    jobs, objs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(obj_dir, s[:-3] + ".o")
+        objs.append(obj)
+        fresh = os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time)
+        if force or extra or not fresh:
+            jobs.append(([nvcc] + COMPILE_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj], s))
+    procs = [(src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd, src in jobs]
+    failed = []
+    for src, proc in procs:
+        log = proc.communicate()[0]
+        if proc.returncode != 0:
+            sys.stderr.write(log)
+            failed.append(src)
+        elif verbose:
+            sys.stderr.write(log)
+    if failed:
+        raise RuntimeError("nvcc failed compiling %s" % ", ".join(failed))
+    res = subprocess.run([nvcc] + LINK_FLAGS + objs + ["-o", LIB_PATH], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libspair_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libspair_b200.so")
     return LIB_PATH
 
 

@@ -66,6 +66,24 @@ struct NeighbourList {
     int dw[SPAIR_MAX_NEIGHBOURS];
 };
 
+// Opt-in to more than 48 KB of dynamic shared memory for `func`, remembered PER DEVICE (the attribute is per device and
+// per function: a process-wide flag would leave a second GPU of the same process without it).  `cache` is a
+// zero-initialised static array owned by the call site, one slot per device ordinal; the attribute only ever grows.
+constexpr int kMaxDevices = 64;
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(F func, size_t bytes, size_t (&cache)[kMaxDevices]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes > cache[dev]) {
+        e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        cache[dev] = bytes;
+    }
+    return cudaSuccess;
+}
+
 inline int grid_for(long long work, int block) {
     long long g = (work + block - 1) / block;
     return (int)(g < 1 ? 1 : g);

@@ -589,11 +589,8 @@ static int launch_fwd(const RenderArgs& a, cudaStream_t st) {
     const size_t smem = group * slot_bytes + (size_t)p.HW * sizeof(float4) +
                         (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
-    static size_t smem_set = 0;   // benign cache: the attribute only ever grows
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(render_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
+    static size_t smem_set[kMaxDevices] = {0};
+    if (ensure_dynamic_smem(render_fwd_kernel<C>, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
     dim3 grid((p.Iw + kRTileW - 1) / kRTileW, (p.Ih + kRTileH - 1) / kRTileH, p.B);
     render_fwd_kernel<C><<<grid, kRThreads, smem, st>>>(p);
     SPAIR_LAUNCH_CHECK();
@@ -611,11 +608,8 @@ static int launch_bwd(const RenderBwdArgs& p, const float* recon, const float* d
     const size_t smem = (size_t)(p.G + 2) * (p.G + 2) * Tex<C>::NF4 * sizeof(float4) +
                         sizeof(float) * ((size_t)kBandPix * ((C + 2) == 3 ? 4 : (C + 2)) + 3 * kBandMaxW + 3 * kBandMaxH + 4 * 32);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(render_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
+    static size_t smem_set[kMaxDevices] = {0};
+    if (ensure_dynamic_smem(render_bwd_kernel<C>, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
     render_bwd_kernel<C><<<(unsigned)((size_t)p.B * p.HW), kRThreads, smem, st>>>(p);
     SPAIR_LAUNCH_CHECK();
 }

@@ -871,11 +871,8 @@ extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, cons
     a.out_box = box; a.z_where = z_where; a.attr = attr; a.depth = depth; a.pres = pres; a.dmean = dmean; a.dstd = dstd;
     const size_t smem = sizeof(float) * (size_t)(kSwRows * kSwKCP + kSwPart + 3 * kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
                         sizeof(int) * 3 * kSwRows;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sweep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static size_t smem_set[kMaxDevices] = {0};
+    if (ensure_dynamic_smem(sweep_fwd_kernel, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
     const int grid = (d->B + d->ipc - 1) / d->ipc;
     sweep_fwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
     SPAIR_LAUNCH_CHECK();
@@ -922,11 +919,8 @@ extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, cons
     a.d_zw = d_zw; a.d_attr = d_attr; a.d_depth = d_depth; a.d_pres = d_pres; a.d_dmean = d_dmean; a.d_dstd = d_dstd;
     const size_t smem = sizeof(float) * (size_t)(kSwPart + 3 * kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) +
                         sizeof(int) * 3 * kSwRows;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sweep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static size_t smem_set[kMaxDevices] = {0};
+    if (ensure_dynamic_smem(sweep_bwd_kernel, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
     const int grid = (d->B + d->ipc - 1) / d->ipc;
     sweep_bwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
     SPAIR_LAUNCH_CHECK();

@@ -94,6 +94,8 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
+RENDER_MAX_TEXELS, RENDER_MAX_CHANNELS = 1024, 4   # spair_render_fwd/bwd: G*G <= 1024, C <= 4 (csrc/render.cu)
+MAX_NEIGHBOURS = 12   # SPAIR_MAX_NEIGHBOURS of include/spair_b200.h (N_LOOKBACK <= 2)
 ABI_VERSION = 2       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
 
 
@@ -193,6 +195,40 @@ def _contig(t, name):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def parallel_branches(device, stream_pool, thunks):
+    """Runs ``thunks[0]`` on the current stream of ``device`` and the others on side streams forked from / joined to it with
+    events (CUDA-graph capture records them as parallel branches).  ``stream_pool(device, n)`` returns n side streams."""
+    cur = torch.cuda.current_stream(device)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    sides = stream_pool(device, len(thunks) - 1)
+    for fn, st in zip(thunks[1:], sides):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            fn()
+    thunks[0]()
+    for st in sides:
+        cur.wait_stream(st)
+
+
+def _device_guarded(fn):
+    """Every launch wrapper below passes raw pointers and ``torch.cuda.current_stream()`` of the CURRENT device to a
+    ``<<<>>>`` launch.  If the tensors live on another device (``SPAIR(...).to('cuda:1')`` without ``set_device``) that
+    would launch on the wrong GPU, so the wrapper switches to the device of its first CUDA tensor argument for the call."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _offsets_array(offsets):
@@ -344,7 +380,8 @@ class PackedSweepWeights:
         for i, w in enumerate(self._sources):
             arr[i].w, arr[i].n, arr[i].k = _ptr(w), self.shapes[i][0], self.shapes[i][1]
             arr[i].fwd, arr[i].bwd = _ptr(self.fwd[i]), _ptr(self.bwd[i])
-        _check(lib().spair_sweep_pack_weights(arr, len(weights), _stream()), "spair_sweep_pack_weights")
+        with torch.cuda.device(weights[0].device):
+            _check(lib().spair_sweep_pack_weights(arr, len(weights), _stream()), "spair_sweep_pack_weights")
 
 
 def sweep_mlp_desc(packed, first, biases, X, H0, H1, Y) -> SweepMLP:
@@ -468,3 +505,11 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
     _check(lib().spair_kl_bwd(_ptr(dmean), _ptr(dstd), _ptr(pres), _ptr(prior_mean), _ptr(prior_std), _ptr(kl_map),
                               _ptr(p_z), _ptr(d_sums), B, HW, A, _ptr(d_dmean), _ptr(d_dstd), _ptr(d_pres), _stream()),
            "spair_kl_bwd")
+
+
+# device guard on every launch wrapper (see _device_guarded)
+for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
+              "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
+              "sweep_bwd", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+    globals()[_name] = _device_guarded(globals()[_name])
+del _name

@@ -140,6 +140,9 @@ class SPAIR(nn.Module):
                              F=int(self.feature_space_dim[0]), A=c.n_attr, P=c.n_pass, C=C, Ih=Ih, Iw=Iw,
                              G=int(c.object_shape[0]))
         plan.fused_forward = plan.fused_backward = "SPAIR_UNFUSED_SWEEP" not in os.environ
+        if plan.G * plan.G > K.RENDER_MAX_TEXELS or C > K.RENDER_MAX_CHANNELS:
+            raise K.SpairKernelError("the fused renderer needs OBJECT_SHAPE[0]^2 <= %d texels and <= %d image channels, got "
+                                     "G=%d, C=%d" % (K.RENDER_MAX_TEXELS, K.RENDER_MAX_CHANNELS, plan.G, C))
         plan.n_hidden = dict(box=len(self.box_network.body) // 2, enc=(len(self.object_encoder) - 1) // 2,
                              z=len(self.z_network.body) // 2, obj=(len(self.obj_network) - 1) // 2)
         plan.to(device)
@@ -174,17 +177,24 @@ class SPAIR(nn.Module):
             ring = 64
             st = SimpleNamespace(wheel=torch.zeros(1, device=device), count=torch.zeros(HW + 1, device=device),
                                  pin=torch.zeros(ring, HW + 2).pin_memory() if device.type == "cuda" else torch.zeros(ring, HW + 2),
-                                 slot=0, ring=ring)
+                                 slot=0, ring=ring, copied=[None] * ring)
             self._step_state = st
         self.global_step = global_step
         wheel_host = exponential_decay(global_step, 'cpu', **self._cfg.wheel)
         self.training_wheel = wheel_host
-        row = st.pin[st.slot]
-        st.slot = (st.slot + 1) % st.ring
+        slot = st.slot
+        st.slot = (slot + 1) % st.ring
+        if st.copied[slot] is not None:
+            st.copied[slot].synchronize()     # the async H2D copy that last read this pinned row has run (host > ring steps ahead)
+        row = st.pin[slot]
         row[0] = wheel_host
         row[1:] = self._count_prior(HW)
         st.wheel.copy_(row[:1], non_blocking=True)
         st.count.copy_(row[1:], non_blocking=True)
+        if device.type == "cuda":
+            if st.copied[slot] is None:
+                st.copied[slot] = torch.cuda.Event()
+            st.copied[slot].record(torch.cuda.current_stream(device))
         return st
 
     def _count_prior(self, HW):

@@ -366,7 +366,10 @@ class CellSweepFunction(torch.autograd.Function):
 
         mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
         max_rows = K.sweep_max_rows() if plan.fused_forward else 0
-        fused = (max_rows >= s.max_cells and all(len(m.H) == 2 and max(m.widths) <= 256 for m in mlps) and G <= 64)
+        # every precondition of spair_sweep_fwd AND spair_sweep_bwd (csrc/sweep.cu), so a shape the kernels would reject
+        # takes the per-wavefront path from the start instead of failing in the middle of backward
+        fused = (max_rows >= s.max_cells and all(len(m.H) == 2 and max(m.widths) <= 256 for m in mlps) and G <= 64
+                 and A + 6 <= 64 and len(s.offsets) <= K.MAX_NEIGHBOURS)
         if fused:
             # ONE persistent launch: a CTA owns `ipc` images and walks all wavefronts (csrc/sweep.cu)
             ipc = max(1, min(2, max_rows // s.max_cells))
@@ -401,10 +404,12 @@ class CellSweepFunction(torch.autograd.Function):
         ctx.plan = plan
         plan.last_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)      # inspection hook for tests (no copy)
         ctx.mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
-        ctx.noise = (eps_where, eps_attr, eps_depth, u_pres, wheel)
-        ctx.x = x
         ctx.n_params = len(params)
-        ctx.save_for_backward(z_where)
+        # the training-wheel scalar lives in a persistent device buffer that the next prepare_step() overwrites: backward
+        # must see THIS forward's value, so it is snapshotted; everything backward reads goes through save_for_backward so
+        # autograd's version counters catch an in-place update (optimizer step) between forward and backward
+        wheel = wheel.clone()
+        ctx.save_for_backward(z_where, x, eps_where, eps_attr, eps_depth, u_pres, wheel, *params)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(box)
         return z_where, attr, depth, pres, dmean, dstd, box
@@ -413,10 +418,8 @@ class CellSweepFunction(torch.autograd.Function):
     def backward(ctx, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd, _d_box):
         plan: SweepPlan = ctx.plan
         s = plan.schedule
-        (z_where,) = ctx.saved_tensors
+        z_where, x, eps_where, eps_attr, eps_depth, u_pres, wheel = ctx.saved_tensors[:7]
         box_mlp, enc_mlp, z_mlp, obj_mlp = ctx.mlps
-        eps_where, eps_attr, eps_depth, u_pres, wheel = ctx.noise
-        x = ctx.x
         dev = z_where.device
         B = z_where.shape[0]
         HW = s.Hc * s.Wc
@@ -492,21 +495,7 @@ class CellSweepFunction(torch.autograd.Function):
         all_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
         for mlp in all_mlps:
             mlp.alloc_weight_grads()
-        if x.is_cuda:
-            cur = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            sides = plan.side_streams(x.device, len(all_mlps) - 1)
-            for mlp, st in zip(all_mlps[1:], sides):
-                st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    mlp.weight_grads()
-            all_mlps[0].weight_grads()
-            for st in sides:
-                cur.wait_stream(st)
-        else:
-            for mlp in all_mlps:
-                mlp.weight_grads()
+        K.parallel_branches(x.device, plan.side_streams, [mlp.weight_grads for mlp in all_mlps])
 
         grads = []
         for mlp, n_heads, head_sizes in ((box_mlp, 2, (8, P)), (enc_mlp, 1, None), (z_mlp, 2, (2, P)), (obj_mlp, 1, None)):

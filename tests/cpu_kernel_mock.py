@@ -25,6 +25,11 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "require_cuda", lambda *a, **k: None)
 
 
+def parallel_branches(device, stream_pool, thunks):
+    for fn in thunks:       # no streams on the CPU: the branches run one after the other
+        fn()
+
+
 def sweep_max_rows():
     return 0        # the fused forward sweep has no test double: host-logic tests exercise the per-wavefront path
 

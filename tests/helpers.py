@@ -92,30 +92,35 @@ def assert_close(actual, expected, what, rtol=RTOL, atol=ATOL):
 
 KINK_FRACTION, KINK_FACTOR = 1e-3, 10.0
 REF_ERR_FACTOR = 2.0
+# Per-test record of how every gradient tensor was judged: {test id: {tensor: {"n", "fp64", "ref_err", "kink", "cos"}}}.
+# tests/conftest.py dumps it to gpurun_out/parity_escapes.json at session end; the committed copy is
+# profiles/r02_parity_escapes.json.  "fp64" / "ref_err" / "kink" count the elements that needed an escape clause.
+ESCAPE_LOG = {}
 
 
-def assert_close_or_as_accurate(actual, ref32, ref64, what, rtol=RTOL, atol=ATOL):
-    """Elementwise: within (rtol, atol) of the reference's fp32 CPU result, OR within (rtol, atol) of the
-    float64 evaluation of the same formulas, OR at least as close to that float64 value as the fp32
-    reference path itself is.  The two escape clauses only matter where the reference's fp32 result is
-    dominated by its own rounding noise (see oracle.forward_backward_fp64).  Returns how many elements
-    needed them.  ReLU / clamp kinks: a pre-activation within one ulp of 0 takes the other branch on the GPU
-    (cuBLAS sums in a different order than MKL) and moves one hidden unit's whole gradient row; at most
-    KINK_FRACTION of a tensor's elements may therefore miss by up to KINK_FACTOR x the tolerance."""
+def grad_escape_report(actual, ref32, ref64, what, rtol=RTOL, atol=ATOL):
+    """Elementwise verdict on a gradient tensor.  An element passes outright when it is within (rtol, atol) of the
+    reference's fp32 CPU result.  Otherwise it may use ONE of three escape clauses, each of which is COUNTED:
+      fp64    — within (rtol, atol) of the float64 evaluation of the same formulas (oracle.forward_backward_fp64);
+      ref_err — at least as close to that float64 value as REF_ERR_FACTOR x the fp32 reference itself is
+                (the reference's own fp32 result is rounding noise there: BCE gradients of 1e12, importance
+                normalisation cancelling nearly equal numbers — SURVEY.md §7);
+      kink    — at most KINK_FRACTION of the tensor may miss by up to KINK_FACTOR x the tolerance (a ReLU / clamp /
+                floor decision within one ulp of its boundary taking the other branch under another summation order).
+    Raises if an element passes none of them.  Returns {"n", "fp64", "ref_err", "kink", "cos"}; callers decide whether
+    non-zero counts are acceptable (``assert_no_escapes``)."""
     a = torch.as_tensor(actual).detach().cpu().double()
     r32 = torch.as_tensor(ref32).detach().cpu().double()
     r64 = torch.as_tensor(ref64).detach().cpu().double()
     assert a.shape == r32.shape == r64.shape, "%s: shapes %s %s %s" % (what, a.shape, r32.shape, r64.shape)
     e32, e64, ref_err = (a - r32).abs(), (a - r64).abs(), (r32 - r64).abs()
     ok32 = e32 <= atol + rtol * r32.abs()
-    # "as accurate as the reference": within REF_ERR_FACTOR x the reference's own distance to the float64 value.
-    # (The sampled-derivative of a bilinear warp is piecewise constant in the box: a sample coordinate within 1e-6 px of
-    # a texel boundary falls on the other side under a different fp32 summation order of the MLPs and moves every
-    # upstream gradient by ~1e-3 of its scale — the same size as the reference's own fp32 error, with another sign.)
-    ok64 = (e64 <= atol + rtol * r64.abs()) | (e64 <= REF_ERR_FACTOR * ref_err)
-    bad = ~(ok32 | ok64)
+    ok64 = e64 <= atol + rtol * r64.abs()
+    okref = e64 <= REF_ERR_FACTOR * ref_err
+    bad = ~(ok32 | ok64 | okref)
+    n_kink = 0
     if 0 < int(bad.sum()) <= KINK_FRACTION * bad.numel() and bool((e64[bad] <= KINK_FACTOR * (atol + rtol * r64.abs()[bad])).all()):
-        print("%s: %d/%d elements attributed to a ReLU/clamp kink (max miss %.2e)" % (what, int(bad.sum()), bad.numel(), float(e64[bad].max())))
+        n_kink = int(bad.sum())
         bad = torch.zeros_like(bad)
     if bool(bad.any()):
         i = int(torch.argmax(torch.where(bad, e64, torch.zeros_like(e64))))
@@ -123,7 +128,39 @@ def assert_close_or_as_accurate(actual, ref32, ref64, what, rtol=RTOL, atol=ATOL
                              "float64 evaluation; worst at flat %d: got %.9g, fp32 ref %.9g, fp64 %.9g"
                              % (what, int(bad.sum()), bad.numel(), rtol, atol, i, a.flatten()[i].item(),
                                 r32.flatten()[i].item(), r64.flatten()[i].item()))
-    return int((~ok32).sum())
+    na, nr = float(a.norm()), float(r64.norm())
+    cos = float((a.flatten() @ r64.flatten()) / (na * nr)) if na > 0 and nr > 0 else 1.0
+    return {"n": int(a.numel()), "fp64": int((~ok32 & ok64).sum()), "ref_err": int((~ok32 & ~ok64 & okref).sum()),
+            "kink": n_kink, "cos": cos}
+
+
+def assert_close_or_as_accurate(actual, ref32, ref64, what, rtol=RTOL, atol=ATOL):
+    """Back-compatible wrapper: number of elements that were not within tolerance of the fp32 reference."""
+    r = grad_escape_report(actual, ref32, ref64, what, rtol, atol)
+    return r["fp64"] + r["ref_err"] + r["kink"]
+
+
+def record_escapes(case, report):
+    ESCAPE_LOG[case] = {k: v for k, v in report.items()}
+
+
+def assert_no_escapes(report, case, max_fraction=0.0, min_cos=1.0 - 1e-6):
+    """``report``: {tensor name: grad_escape_report()}.  With max_fraction == 0 every element of every gradient tensor
+    must be within (rtol, atol) of the fp32 reference itself — the plain criterion of BASELINE.json's north_star.  Where
+    escapes are tolerated the caller states the budget (fraction of a tensor's elements) and it is enforced here.
+    Every tensor must also point the same way as the float64 gradient (cosine)."""
+    problems = []
+    for k, r in report.items():
+        used = r["fp64"] + r["ref_err"] + r["kink"]
+        if used > max_fraction * r["n"]:
+            problems.append("%s: %d/%d elements needed an escape clause (fp64 %d, ref_err %d, kink %d); budget %.2g"
+                            % (k, used, r["n"], r["fp64"], r["ref_err"], r["kink"], max_fraction))
+        if r["cos"] < min_cos:
+            problems.append("%s: cosine with the float64 gradient %.9f < %.9f" % (k, r["cos"], min_cos))
+    if problems and os.environ.get("SPAIR_PARITY_REPORT_ONLY"):      # first look at a new kernel: record, do not fail
+        print("%s:\n%s" % (case, "\n".join(problems)))
+        return
+    assert not problems, "%s:\n%s" % (case, "\n".join(problems))
 
 
 def check_model_against_golden(net, g, device):
@@ -151,7 +188,7 @@ def check_model_against_golden(net, g, device):
     for n, p in net.dist_param.items():
         assert_close(p["mean"], g["dist_mean/" + n], "dist mean " + n)
         assert_close(p["sigma"], g["dist_std/" + n], "dist sigma " + n)
-    worst, failures = {}, []
+    report, failures = {}, []
     for k, p in net.named_parameters():
         if "gnone/" + k in g.files:
             assert p.grad is None, "%s must not receive a gradient (reference: grad is None)" % k
@@ -163,14 +200,12 @@ def check_model_against_golden(net, g, device):
         # gradient tolerance is relative to the scale of the tensor (individual entries cancel to ~0)
         scale = float(g["gstat/" + k][1]) / max(np.sqrt(gr.numel()), 1.0)
         try:
-            n64 = assert_close_or_as_accurate(gr[idx], want, g["g64val/" + k], "grad " + k, rtol=RTOL, atol=ATOL + RTOL * scale)
-            if n64:
-                print("grad %s: %d/%d sampled elements judged against the float64 evaluation" % (k, n64, idx.numel()))
-            else:
-                stat = np.array([gr.double().sum().item(), gr.double().norm().item()])
-                assert abs(stat[1] - g["gstat/" + k][1]) <= 1e-4 * g["gstat/" + k][1] + 1e-7, "grad norm of %s" % k
+            report[k] = grad_escape_report(gr[idx], want, g["g64val/" + k], "grad " + k, rtol=RTOL, atol=ATOL + RTOL * scale)
+            # full-tensor check: the L2 norm of the WHOLE gradient (the samples above cover <= 1024 elements)
+            norm = gr.double().norm().item()
+            assert abs(norm - g["gstat/" + k][1]) <= 1e-4 * g["gstat/" + k][1] + 1e-7, \
+                "grad norm of %s: %.9g vs reference %.9g" % (k, norm, g["gstat/" + k][1])
         except AssertionError as e:
             failures.append(str(e))
-        worst[k] = float((gr[idx] - want).abs().max())
     assert not failures, "\n".join(failures)
-    return worst
+    return report

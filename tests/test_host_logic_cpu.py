@@ -14,14 +14,16 @@ def test_model_orchestration_matches_reference_golden_tiny(monkeypatch, step):
     cpu_kernel_mock.install(monkeypatch)
     net = helpers.build_model("tiny")
     g = helpers.load_golden("model_tiny_step%d.npz" % step)
-    helpers.check_model_against_golden(net, g, "cpu")
+    report = helpers.check_model_against_golden(net, g, "cpu")
+    helpers.assert_no_escapes(report, "host logic tiny step %d" % step)
 
 
 def test_model_orchestration_matches_reference_golden_A(monkeypatch):
     cpu_kernel_mock.install(monkeypatch)
     net = helpers.build_model("A")
     g = helpers.load_golden("model_A_step1001.npz")
-    helpers.check_model_against_golden(net, g, "cpu")
+    report = helpers.check_model_against_golden(net, g, "cpu")
+    helpers.assert_no_escapes(report, "host logic A step 1001")
 
 
 def test_model_orchestration_lookback2_matches_oracle(monkeypatch):

@@ -80,3 +80,24 @@ def test_metrics_match_reference():
         assert torch.allclose(ns.metric.batch_jaccard(box_a, box_b), ours.batch_jaccard(box_a, box_b), rtol=1e-6, atol=1e-7)
     finally:
         cfg.BATCH_SIZE = saved
+
+
+def test_checkpoint_saved_by_the_reference_loads_into_the_drop_in(tmp_path):
+    """reference train.py:85-90 saves ``spair_net.state_dict()``; the drop-in model must load that file strictly (same
+    keys, shapes, dtypes) and the other way round."""
+    from tests import helpers
+    ns = rh.load_reference({})
+    ref = rh.build_reference_model(ns, seed=11)
+    path = str(tmp_path / "step_1000.pkl")
+    torch.save(ref.state_dict(), path)
+    ours = helpers.build_model("A", seed=3)
+    before = ours.box_network.body[0].weight.detach().clone()
+    missing, unexpected = ours.load_state_dict(torch.load(path), strict=True)
+    assert not missing and not unexpected
+    assert not torch.equal(before, ours.box_network.body[0].weight)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
+    ref2 = rh.build_reference_model(rh.load_reference({}), seed=5)
+    ref2.load_state_dict(ours.state_dict(), strict=True)
+    for k, v in ref2.state_dict().items():
+        assert torch.equal(v, ref.state_dict()[k]), k

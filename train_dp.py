@@ -61,6 +61,8 @@ def main():
     ap.add_argument("--resume", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--log-every", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=1000, help="noise / scene streams are a function of (seed, rank, step)")
+    ap.add_argument("--save-final", default=None, help="write the model state_dict here after the last step (rank 0)")
     args = ap.parse_args()
 
     rank, world, local_rank = dp.init_distributed()
@@ -75,7 +77,9 @@ def main():
         except ImportError:
             pass
 
-    torch.backends.cudnn.benchmark = True                         # fixed shapes: fastest fp32 conv algorithms
+    # fixed shapes: let cuDNN pick its fastest fp32 conv algorithms — unless bitwise reproducibility was asked for
+    # (SPAIR_DETERMINISTIC=1: the autotuner may pick different algorithms in different processes)
+    torch.backends.cudnn.benchmark = "SPAIR_DETERMINISTIC" not in os.environ
     torch.manual_seed(3)                                          # train.py:39
     net = SPAIR(cfg.INPUT_IMAGE_SHAPE, writer if args.eager else _NullWriter(), dev).to(dev)
     ddp = dp.DataParallelSPAIR(net, world_size=world)
@@ -90,15 +94,14 @@ def main():
         if rank == 0:
             print("resumed from step", ck["step"])
 
-    loader = None
+    loader, sampler, epoch = None, None, 0
     if args.hdf5:                                                 # the reference's dataset, one DataLoader per rank
         dataset = SimpleScatteredMNISTDataset(args.hdf5)
         sampler = torch_data.distributed.DistributedSampler(dataset, world, rank) if world > 1 else None
         loader = torch_data.DataLoader(dataset, batch_size=args.batch, pin_memory=True, num_workers=2, drop_last=True,
                                        sampler=sampler)
         it = iter(loader)
-    data_gen = torch.Generator(device=dev).manual_seed(1234 + 7919 * rank)    # procedural scenes made on the device
-    torch.manual_seed(1000 + rank)                                # per-rank noise stream
+    data_gen = torch.Generator(device=dev)                        # procedural scenes made on the device
     gstep, t0, seen = None, time.time(), 0
     last = step + args.steps
     while step < last:
@@ -106,16 +109,23 @@ def main():
             try:
                 x_image, y_bbox, y_count = next(it)
             except StopIteration:
+                epoch += 1
+                if sampler is not None:
+                    sampler.set_epoch(epoch)      # a new shuffle every epoch (DistributedSampler repeats its order otherwise)
                 it = iter(loader)
                 continue
             x_image = x_image.float()
         else:
+            data_gen.manual_seed(1234 + 7919 * rank + 104729 * step)
             x_image, y_bbox, y_count = scattered_sprites_gpu(args.batch, cfg.INPUT_IMAGE_SHAPE, dev, data_gen)
+        if gstep is None and not args.eager:
+            gstep = GraphedTrainStep(net, x_image.to(dev), bucket=ddp.bucket, global_step=step)
+        # the latent noise of a step is a function of (seed, rank, step), not of how many draws came before it: a captured
+        # graph reads the generator's seed at replay, so re-seeding here makes `--resume` continue the SAME trajectory
+        torch.cuda.manual_seed(args.seed + rank + 1000003 * step)
         if args.eager:
             out = ddp.step(x_image.to(dev, non_blocking=True), step)
         else:
-            if gstep is None:
-                gstep = GraphedTrainStep(net, x_image.to(dev), bucket=ddp.bucket, global_step=step)
             out = gstep(x_image, step)                            # async H2D + one graph replay
             if world > 1:
                 ddp.bucket.all_reduce()
@@ -138,6 +148,8 @@ def main():
                        os.path.join(args.ckpt_dir, "step_%d.pt" % step))
         step += 1
     torch.cuda.synchronize()
+    if args.save_final and rank == 0:
+        torch.save(net.state_dict(), args.save_final)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
