@@ -63,6 +63,17 @@ def measured_tf32x3_peak():
         return 1590.0 / 6.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16 / 2 / 3)"
 
 
+def measured_fp32_peak():
+    """fp32 FFMA peak of the SIMT pipes: 148 SMs x 128 lanes x 2 FLOP x the maximum SM clock the driver measured."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mhz = float(json.load(f)["sm_max_mhz"])
+        src = "148 SMs x 128 FFMA lanes x 2 x %.0f MHz (MEASURED_PEAKS.json sm_max_mhz)" % mhz
+    except Exception:
+        mhz, src = 1965.0, "148 SMs x 128 FFMA lanes x 2 x 1965 MHz (nominal)"
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12, src
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -137,8 +148,16 @@ def kernel_roofline(net, x, steps=20):
     HW = L.Hc * L.Wc
     G = net._cfg.object_shape[0]
     N = B * HW
+    from spair_pytorch_b200 import ops
+    decoded = ops.USE_TENSOR_CORE_GEMM      # the renderer consumes sigmoid-decoded texel records (ops.DecoderFunction)
+    lin = [m for m in net.object_decoder if isinstance(m, torch.nn.Linear)]
     with torch.no_grad():
-        logits = net.object_decoder(L.attr.reshape(N, -1)).contiguous()
+        if decoded:
+            logits = ops.DecoderFunction.apply(L.attr.reshape(N, -1), *(p for m in lin for p in (m.weight, m.bias)), C + 1,
+                                               net._cfg.scales)
+        else:
+            logits = net.object_decoder(L.attr.reshape(N, -1)).contiguous()
+        dec_h1 = net.object_decoder[:-1](L.attr.reshape(N, -1)).contiguous()
     zw, zd, zp = L.z_where.reshape(N, 4).contiguous(), L.depth.reshape(-1).contiguous(), L.pres.reshape(-1).contiguous()
     recon = torch.empty(B, C, I, I, device=dev)
     denom = torch.empty(B, I, I, device=dev)
@@ -153,10 +172,11 @@ def kernel_roofline(net, x, steps=20):
     scales = net._cfg.scales
 
     def t_render_fwd():
-        K.render_fwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, x, partial)
+        K.render_fwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, x, partial, decoded)
 
     def t_render_bwd():
-        K.render_bwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, None, x, None, gs, d_logits, d_zw, d_zd, d_zp)
+        K.render_bwd(logits, zw, zd, zp, B, HW, C, G, I, I, scales, recon, denom, None, x, None, gs, d_logits, d_zw, d_zd, d_zp,
+                     decoded)
 
     def t_glimpse_fwd():
         K.glimpse_fwd(x, L.z_where, cells, B, HW, G, G, glimpses)
@@ -211,11 +231,39 @@ def kernel_roofline(net, x, steps=20):
         out[name] = {"ms": ms, "bytes": nbytes, "achieved": gbs, "frac": gbs / peak}
     for v in out.values():
         v.update(bound="hbm", unit="GB/s", peak=peak)
-    # the fused cell sweep: ONE persistent launch per direction holding all wavefronts x 4 three-layer MLPs.  It is a chain
-    # of small dense layers (3xTF32 tensor-core MMAs fed by a TMA weight ring), not HBM work: reported as algorithmic fp32
-    # FLOPs (2 x MACs x rows, NOT counting the 3 MMAs per product) against the fp32-equivalent tensor peak.  Timed with CUDA
-    # events placed directly around the two launches inside the operator.
-    from spair_pytorch_b200 import ops
+    tpeak, tpeak_src = measured_tf32x3_peak()
+    # the decoder's output layer on the tcgen05 GEMM (csrc/gemm.cu): y = x W^T with the texel epilogue, dx = dy W, dW = dy^T x.
+    # Algorithmic fp32 FLOPs (2 M N K, NOT counting the 3 MMAs per product) against the fp32-equivalent tensor peak.
+    if decoded and K.gemm_supported(dec_h1, lin[-1].weight):
+        w2, b2 = lin[-1].weight.detach(), lin[-1].bias.detach()
+        tex = torch.empty(N, w2.shape[0], device=dev)
+        d_h1, d_w2 = torch.empty_like(dec_h1), torch.empty_like(w2)
+        d_logits.normal_()
+        gemms = {"decoder_out_fwd": lambda: K.gemm3x(dec_h1, True, w2, True, tex, b2, epilogue=K.GEMM_EPI_TEXEL, period=C + 1,
+                                                     scales=scales),
+                 "decoder_out_dgrad": lambda: K.gemm3x(d_logits.view(N, -1), True, w2, False, d_h1),
+                 "decoder_out_wgrad": lambda: K.gemm3x(d_logits.view(N, -1), False, dec_h1, False, d_w2)}
+        for name, fn in gemms.items():
+            for _ in range(3):
+                fn()
+            times = []
+            for _ in range(steps):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                times.append(e0.elapsed_time(e1))
+            ms = statistics.mean(times)
+            fl = 2.0 * N * w2.shape[0] * w2.shape[1]
+            out[name] = {"ms": ms, "flops": fl, "achieved": fl / (ms * 1e-3) / 1e12, "frac": fl / (ms * 1e-3) / 1e12 / tpeak,
+                         "bound": "tensor", "unit": "TFLOP/s", "peak": tpeak,
+                         "note": "tcgen05.mma kind::tf32, 3 MMAs per fp32-accurate product (hi*hi + hi*lo + lo*hi)"}
+    # the fused cell sweep: ONE persistent launch per direction holding all wavefronts x 4 three-layer MLPs, <= 16 rows per
+    # CTA: a latency-bound chain of small dense layers on the fp32 SIMT pipes (a 3xTF32 mma.sync variant was measured 2x
+    # slower, profiles/r02_sweep_mma_variant_rejected.md).  Reported as algorithmic fp32 FLOPs against the fp32 FFMA peak
+    # (148 SMs x 128 lanes x 2 FLOP x max SM clock).  Timed with CUDA events around the two launches inside the operator.
     plan = net._plan
     sweep_ms = {"fwd": [], "bwd": []}
     feat = net.backbone(x).detach().requires_grad_(True)
@@ -234,15 +282,15 @@ def kernel_roofline(net, x, steps=20):
                 if k in ev:
                     sweep_ms[k].append(ev[k][0].elapsed_time(ev[k][1]))
     macs = sum(w.shape[0] * w.shape[1] for m in plan.last_mlps for w in m.W)
-    tpeak, tpeak_src = measured_tf32x3_peak()
+    fpeak, fpeak_src = measured_fp32_peak()
     for k, label in (("fwd", "sweep_fwd"), ("bwd", "sweep_bwd")):
         if sweep_ms[k]:
             ms = statistics.mean(sweep_ms[k])
             tf = 2 * macs * N / (ms * 1e-3) / 1e12
-            out[label] = {"ms": ms, "flops": 2 * macs * N, "achieved": tf, "frac": tf / tpeak, "bound": "tensor",
-                          "unit": "TFLOP/s", "peak": tpeak,
+            out[label] = {"ms": ms, "flops": 2 * macs * N, "achieved": tf, "frac": tf / fpeak, "bound": "fp32",
+                          "unit": "TFLOP/s", "peak": fpeak,
                           "note": "persistent fused cell sweep (%s): context + 4 MLPs + heads + glimpse for all wavefronts "
-                                  "in one launch; the chain of %d dependent wavefronts x 12 layers bounds it, not the MMA rate"
+                                  "in one launch; the chain of %d dependent wavefronts x 12 layers bounds it, not the FFMA rate"
                                   % (k, plan.schedule.n_wavefronts)}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same
     # kernels at this shape (B=256, C=1, I=128, 121 cells, G=28)
@@ -253,7 +301,7 @@ def kernel_roofline(net, x, steps=20):
         r = {"bound": v["bound"], "kernel": name, "achieved": v["achieved"], "peak": v["peak"], "unit": v["unit"],
              "frac": v["frac"], "traffic": ncu_traffic.get(name, (None, None))[0],
              "traffic_source": ncu_traffic.get(name, (None, None))[1],
-             "peak_source": peak_src if v["bound"] == "hbm" else tpeak_src, "ms_per_launch": v["ms"],
+             "peak_source": {"hbm": peak_src, "tensor": tpeak_src, "fp32": fpeak_src}[v["bound"]], "ms_per_launch": v["ms"],
              "timing": "CUDA events on the launching stream, 256 MB L2 flush between launches, mean of %d" % steps}
         if v["bound"] == "hbm":
             r["algorithmic_bytes_per_launch"] = v["bytes"]
@@ -499,7 +547,7 @@ def run_ours(args):
             "config": {"workload": "BASELINE %s, batch %d per GPU, procedural scattered sprites, step = zero_grad+fwd+bwd+Adam%s"
                                    % (workload_name(args.config), B, "+NCCL grad allreduce" if world > 1 else ""),
                        "per_gpu_batch": B, "global_batch": world * B, "objects_per_image": HW, "global_step": STEP0,
-                       "parallelism": "dp%d" % world, "tf32": "3xTF32 split (fp32-accurate) inside the fused sweep/decoder kernels; "
+                       "parallelism": "dp%d" % world, "tf32": "3xTF32 split (fp32-accurate) tcgen05 GEMMs for the decoder MLP and the weight gradients; sweep MLPs fp32 SIMT; "
                                                               "cuDNN/cuBLAS TF32 off",
                        "launch": "eager" if args.eager else "fwd+bwd replayed from one CUDA graph; allreduce + fused Adam eager",
                        "l2": "per-step working set (~2.3 KB x %d objects x fwd+bwd buffers, > 1 GB) exceeds the 126 MB L2; "

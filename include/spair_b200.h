@@ -26,7 +26,7 @@ extern "C" {
 
 #define SPAIR_ERR_INVALID (-1)
 #define SPAIR_MAX_NEIGHBOURS 12
-#define SPAIR_ABI_VERSION 2   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows */
+#define SPAIR_ABI_VERSION 3   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows; 3: tcgen05 GEMM */
 
 int spair_abi_version(void);
 
@@ -195,21 +195,26 @@ int spair_paste_bwd(const float* image, const float* z_where, int n, int C, int 
  * ---------------------------------------------------------------------------------- */
 int spair_render_num_tiles(int B, int Ih, int Iw);  /* length of bce_partial */
 
-int spair_render_fwd(const float* logits,                 /* [B*HW, G, G, C+1] raw decoder output */
+int spair_render_fwd(const float* logits,                 /* [B*HW, G, G, C+1] raw decoder output, or texel records */
                      const float* z_where,                /* [B*HW,4] */
                      const float* z_depth, const float* z_pres, /* [B*HW] */
                      int B, int HW, int C, int G, int Ih, int Iw,
                      float obj_scale, float alpha_scale, float alpha_bias,
+                     int decoded,                         /* 0: `logits` are raw; 1: texel records written by spair_gemm3x with
+                                                             SPAIR_GEMM_EPI_TEXEL (colour = sigma(obj_scale * l), alpha channel =
+                                                             1 - sigma(alpha_scale * l + alpha_bias)); the scales are then unused
+                                                             in the forward and only scale the gradient in the backward */
                      float* recon,                        /* [B,C,Ih,Iw] */
                      float* denom,                        /* [B,Ih,Iw]: sum_n(importance_n + 1e-9), negated where the clamp at 1 was active */
                      const float* target, float* bce_partial, /* both NULL or both set */
                      void* stream);
 
 /* Gradient wrt recon is d_recon (may be NULL) + bce_scale * dBCE/drecon(recon, target)
- * (target may be NULL).  gs_ws is a [B,C+1,Ih,Iw] workspace. */
+ * (target may be NULL).  gs_ws is a [B,C+1,Ih,Iw] workspace.  d_logits is the gradient
+ * wrt the RAW logits in both modes (with decoded = 1 the sigmoid derivative comes from the records). */
 int spair_render_bwd(const float* logits, const float* z_where, const float* z_depth,
                      const float* z_pres, int B, int HW, int C, int G, int Ih, int Iw,
-                     float obj_scale, float alpha_scale, float alpha_bias,
+                     float obj_scale, float alpha_scale, float alpha_bias, int decoded,
                      const float* recon, const float* denom,
                      const float* d_recon, const float* target, const float* bce_scale /* device scalar or NULL (=1) */,
                      float* gs_ws,
@@ -343,6 +348,32 @@ int spair_stem_conv_bwd(const float* x, const float* y, const float* dy, int B, 
 /* out[r][:] = row[:] for r < rows (vectorised when cols % 4 == 0): pre-fills the decoder's [B*HW, G*G*(C+1)] logits
  * (reference models.py:165,477) with the bias so that the output GEMM runs with beta = 1. */
 int spair_broadcast_rows(const float* row, int rows, int cols, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * D*  the path's own dense contractions on the tcgen05 tensor cores at fp32 accuracy (3xTF32 split precision, fp32
+ * accumulation in TMEM): the decoder MLP `object_decoder` (reference models.py:165,474-481, modules.py:124-165) and the
+ * weight gradients of the per-object MLPs.  C[M,N] = A . B (+ bias) with the reduction over K:
+ *   a_kmajor = 1: A is stored [M][lda] (K contiguous);  0: stored [K][lda] (M contiguous)
+ *   b_kmajor = 1: B is stored [N][ldb] (K contiguous);  0: stored [K][ldb] (N contiguous)
+ * so y = x W^T is (1,1), dx = dy W is (1,0) and dW = dy^T x is (0,0) on the tensors as torch stores them.
+ * lda, ldb must be multiples of 4 floats and A, B 16-byte aligned (TMA).  epilogue (splits == 1 only):
+ *   SPAIR_GEMM_EPI_NONE   C = acc + bias
+ *   SPAIR_GEMM_EPI_RELU   C = max(acc + bias, 0)                                  (build_MLP hidden layers)
+ *   SPAIR_GEMM_EPI_TEXEL  C = sigma(s * (acc + bias) + b) per channel of a `period`-channel texel: channels
+ *                         0..period-2 use (s_colour, 0), the last one (s_alpha, b_alpha), sigma(x) = 1/(exp(-x)+1)
+ *                         — the per-texel transcendental part of SPAIR._render (models.py:485-493), so the renderer
+ *                         reads decoded texel records and the logits never reach HBM.
+ * splits > 1 (long reductions with a small output): partial products go to `workspace` ([splits][M][N] floats) and are
+ * summed in a fixed order by a second launch; spair_gemm_splits() returns the split count the library would pick.
+ * ---------------------------------------------------------------------------------- */
+#define SPAIR_GEMM_EPI_NONE 0
+#define SPAIR_GEMM_EPI_RELU 1
+#define SPAIR_GEMM_EPI_TEXEL 2
+int spair_gemm_block_n(int N, int b_kmajor);
+int spair_gemm_splits(int M, int N, int K);
+int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M,
+                 int N, int K, const float* bias /* [N] or NULL */, int epilogue, int period, float s_colour, float s_alpha,
+                 float b_alpha, float* workspace, int splits, void* stream);
 
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);

@@ -1,0 +1,521 @@
+// tcgen05 GEMM for the path's own dense contractions (the decoder MLP, reference models.py:165,474-500, and the weight
+// gradients of the five per-object MLPs, modules.py:124-165), fp32 in / fp32 out at fp32 accuracy.
+//
+// The 5th-generation tensor cores have no fp32 input type, and plain TF32 (10 mantissa bits) misses the parity tolerance
+// (rtol 1e-4) by an order of magnitude.  Each operand is therefore split in shared memory into x = hi + lo, hi = x rounded
+// to TF32 and lo = x - hi (exact in fp32), and every k-step issues three MMAs into the same TMEM accumulator:
+// hi*hi + hi*lo + lo*hi ("3xTF32"; the dropped lo*lo term is 2^-22 relative).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: raw fp32 tiles global -> shared (128-byte swizzle), one mbarrier per ring stage
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8), accumulators in TMEM,
+//               double-buffered (2 x 256 columns) so that the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2-9   splitters: raw tile -> hi (in place) and lo (second buffer), fence.proxy.async, signal the MMA warp
+//   warps 10-17 epilogue: tcgen05.ld TMEM -> registers, bias / ReLU / texel decode, transpose through shared memory,
+//               coalesced 128-bit global stores (two warps per TMEM lane quarter, each takes half of the columns)
+// Either operand may be K-major (reduction index contiguous in memory) or MN-major, so that y = x W^T, dx = dy W and
+// dW = dy^T x all run on the stored tensors without a transposed copy.  A reduction that is much longer than the output
+// is wide (the weight gradients: K = B*HW rows) is split over CTAs into a workspace and summed in a fixed order by a
+// second kernel (deterministic; no atomics).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace spair {
+namespace gemm {
+
+constexpr int BM = 128;          // rows of one output tile = TMEM lanes
+constexpr int BK = 32;           // floats per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // k per tcgen05.mma.kind::tf32
+constexpr int kSplitWarps = 8, kEpiWarps = 8;
+constexpr int kSplitWarp0 = 2, kEpiWarp0 = kSplitWarp0 + kSplitWarps;
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 18 warps
+constexpr int kStgPitch = 20;     // floats per row of the epilogue transpose buffer (32 rows x 16 columns per pass)
+constexpr int kAccumCols = 256;  // TMEM columns per accumulator buffer (two buffers = the whole 512-column TMEM)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"; same bit layout as cute::UMMA::SmemDescriptor):
+// start address >> 4 in [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
+// [46,48), layout type in [61,64): 2 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte
+// chunks, Swizzle<2,5,2>: the only swizzled layout the hardware accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)layout << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), majors at bits
+// 15 / 16 (0 = K-major), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t instr_desc(int n, bool a_kmajor, bool b_kmajor) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_kmajor ? 0u : 1u) << 15) | ((b_kmajor ? 0u : 1u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Params {
+    int M, N, K;          // output rows / columns, reduction length
+    int splits, k_per_split;   // k_per_split is a multiple of BK
+    float* C;             // [M, ldc] when splits == 1, else workspace [splits][M][N] (ldc = N)
+    int ldc;
+    const float* bias;    // [N] or nullptr (applied here only when splits == 1)
+    int epilogue;         // SPAIR_GEMM_EPI_*
+    int period;           // texel decode: channels per texel (C + 1)
+    float s_colour, s_alpha, b_alpha;
+    int debug;            // diagnostics (SPAIR_GEMM_DEBUG): 1 = splitters skip their work, 2 = one MMA per k-step, 4 = no stores
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int kStageA = BM * BK * 4, kStageB = BN * BK * 4;
+    static constexpr int kStage = 2 * (kStageA + kStageB);   // hi + lo of both operands
+    static constexpr int kStages = (200 * 1024) / kStage < 4 ? (200 * 1024) / kStage : 4;
+    static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */ + kEpiWarps * 32 * kStgPitch * 4;
+};
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // stage s: [A hi | B hi | A lo | B lo]
+    auto a_hi = [&](int s) { return base + s * C::kStage; };
+    auto b_hi = [&](int s) { return base + s * C::kStage + C::kStageA; };
+    auto a_lo = [&](int s) { return base + s * C::kStage + C::kStageA + C::kStageB; };
+    auto b_lo = [&](int s) { return base + s * C::kStage + 2 * C::kStageA + C::kStageB; };
+    const uint32_t bars = base + C::kStages * C::kStage;
+    auto bar_full = [&](int s) { return bars + 8 * s; };
+    auto bar_ready = [&](int s) { return bars + 8 * (C::kStages + s); };
+    auto bar_empty = [&](int s) { return bars + 8 * (2 * C::kStages + s); };
+    auto bar_acc_full = [&](int a) { return bars + 8 * (3 * C::kStages + a); };
+    auto bar_acc_empty = [&](int a) { return bars + 8 * (3 * C::kStages + 2 + a); };
+    const uint32_t tmem_slot = bars + 8 * (3 * C::kStages + 4);
+    const uint32_t stage_out = bars + 256;   // epilogue transpose buffers: 4 warps x 32 rows x kStgPitch floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int n_work = m_tiles * n_tiles * p.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_ready(s), kSplitWarps);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_acc_full(a), 1);
+            mbar_init(bar_acc_empty(a), kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * kAccumCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // work item -> (m tile, n tile, split); n fastest so that concurrently running CTAs share the A rows in L2
+    auto decode = [&](int w, int& mt, int& nt, int& sp) {
+        nt = w % n_tiles;
+        int r = w / n_tiles;
+        mt = r % m_tiles;
+        sp = r / m_tiles;
+    };
+    auto k_blocks_of = [&](int sp) {
+        int k0 = sp * p.k_per_split;
+        int k1 = min(p.K, k0 + p.k_per_split);
+        return (k1 - k0 + BK - 1) / BK;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_n = k_blocks_of(sp), k_base = sp * p.k_per_split;
+                for (int kb = 0; kb < kb_n; ++kb) {
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    mbar_expect_tx(bar_full(stage), C::kStageA + C::kStageB);
+                    const int k0 = k_base + kb * BK;
+                    if (A_K) {
+                        tma_load_2d(a_hi(stage), &map_a, bar_full(stage), k0, mt * BM);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(stage) + j * 4096, &map_a, bar_full(stage), mt * BM + 32 * j, k0);
+                    }
+                    if (B_K) {
+                        tma_load_2d(b_hi(stage), &map_b, bar_full(stage), k0, nt * BN);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(stage) + j * 4096, &map_b, bar_full(stage), nt * BN + 32 * j, k0);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer --------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(BN, A_K, B_K);
+            // K-major (SWIZZLE_128B): 8-row groups of 1024 B (SBO), k-step of 8 floats = +32 B inside the swizzle row.
+            // MN-major (SWIZZLE_128B_BASE32B): a TMA box is 32 k-rows x 32 columns (128 B per row): 32-column atoms of
+            // 4096 B (LBO), 4-k groups of 512 B (SBO), k-step of 8 rows = +1024 B.
+            constexpr uint32_t a_lbo = A_K ? 16 : 4096, b_lbo = B_K ? 16 : 4096;
+            constexpr uint32_t a_sbo = A_K ? 1024 : 512, b_sbo = B_K ? 1024 : 512;
+            constexpr uint32_t a_lay = A_K ? 2 : 1, b_lay = B_K ? 2 : 1;
+            constexpr uint32_t a_step = A_K ? UMMA_K * 4 : 1024, b_step = B_K ? UMMA_K * 4 : 1024;
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_n = k_blocks_of(sp);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_acc_empty(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * kAccumCols;
+                for (int kb = 0; kb < kb_n; ++kb) {
+                    mbar_wait(bar_ready(stage), phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        const uint64_t dah = smem_desc(a_hi(stage) + kk * a_step, a_lbo, a_sbo, a_lay);
+                        const uint64_t dal = smem_desc(a_lo(stage) + kk * a_step, a_lbo, a_sbo, a_lay);
+                        const uint64_t dbh = smem_desc(b_hi(stage) + kk * b_step, b_lbo, b_sbo, b_lay);
+                        const uint64_t dbl = smem_desc(b_lo(stage) + kk * b_step, b_lbo, b_sbo, b_lay);
+                        if (!(p.debug & 2)) {
+                            umma_tf32(d, dal, dbh, idesc, (kb | kk) != 0);
+                            umma_tf32(d, dah, dbl, idesc, 1);
+                            umma_tf32(d, dah, dbh, idesc, 1);
+                        } else {
+                            umma_tf32(d, dah, dbh, idesc, (kb | kk) != 0);
+                        }
+                    }
+                    umma_commit(bar_empty(stage));   // the stage may be refilled once these MMAs have read it
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_acc_full(acc));
+            }
+        }
+    } else if (warp < kEpiWarp0) {
+        // ------------------------------------------------ splitters ---------------------------------------------------
+        const int t = threadIdx.x - kSplitWarp0 * 32;
+        constexpr int kChunks = (C::kStageA + C::kStageB) / 16;
+        constexpr uint32_t kLoOff = C::kStageA + C::kStageB;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int kb_n = k_blocks_of(sp);
+            for (int kb = 0; kb < kb_n; ++kb) {
+                mbar_wait(bar_full(stage), phase);
+                const uint32_t s0 = a_hi(stage);
+#pragma unroll 4
+                for (int c = t; c < ((p.debug & 1) ? 0 : kChunks); c += kSplitWarps * 32) {
+                    const uint32_t addr = s0 + c * 16;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+                    uint32_t h0 = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u, h1 = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
+                    uint32_t h2 = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u, h3 = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
+                    // lo = x - hi is exact in fp32 (13 significant bits); rounded to TF32 here (the tensor core would truncate it)
+                    const uint32_t l0 = (__float_as_uint(v.x - __uint_as_float(h0)) + 0x1000u) & 0xffffe000u;
+                    const uint32_t l1 = (__float_as_uint(v.y - __uint_as_float(h1)) + 0x1000u) & 0xffffe000u;
+                    const uint32_t l2 = (__float_as_uint(v.z - __uint_as_float(h2)) + 0x1000u) & 0xffffe000u;
+                    const uint32_t l3 = (__float_as_uint(v.w - __uint_as_float(h3)) + 0x1000u) & 0xffffe000u;
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + kLoOff), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(stage));
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue ----------------------------------------------------
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int e = warp - kEpiWarp0;
+        constexpr int kChunks32 = BN / 32, kHalf = (kChunks32 + 1) / 2;
+        const int c_begin = (e < 4) ? 0 : kHalf * 32, c_end = (e < 4) ? kHalf * 32 : BN;   // two warps share a lane quarter
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_acc_full(acc), acc_phase);
+            tc_fence_after();
+            const int row0 = mt * BM + q * 32;
+            const int n0 = nt * BN;
+            float* cbase = p.C + (size_t)sp * p.M * p.N;
+            const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
+            const uint32_t stg = stage_out + e * (32 * kStgPitch * 4);
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccumCols + c0, r);
+                if (n0 + c0 >= p.N || (p.debug & 4)) continue;   // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.splits == 1) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < p.N) v[j] += __ldg(p.bias + n0 + c0 + j);
+                    }
+                    if (p.epilogue == SPAIR_GEMM_EPI_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    } else if (p.epilogue == SPAIR_GEMM_EPI_TEXEL) {
+                        // reference models.py:485-493: colour = sigma(OBJ_LOGIT_SCALE * l), alpha = sigma(ALPHA_LOGIT_SCALE * l
+                        // + ALPHA_LOGIT_BIAS), sigma(x) = 1 / (exp(-x) + 1) (modules.py:186-187)
+                        int ch = (n0 + c0) % p.period;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const bool is_alpha = ch == p.period - 1;
+                            const float x = is_alpha ? __fadd_rn(__fmul_rn(v[j], p.s_alpha), p.b_alpha) : __fmul_rn(v[j], p.s_colour);
+                            // the alpha channel stores the complement 1 - sigma(x) = e / (e + 1): the +5 bias saturates alpha
+                            // near 1, and the renderer's backward needs sigma'(x) = s (1 - s) to full relative accuracy
+                            const float e = __expf(-x);
+                            v[j] = __fdividef(is_alpha ? e : 1.0f, e + 1.0f);
+                            if (++ch == p.period) ch = 0;
+                        }
+                    }
+                }
+                // thread = row in TMEM; transpose through shared memory (two passes of 16 columns) so that every store
+                // instruction writes whole 64-byte row segments instead of 16 bytes in each of 32 rows
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (lane * kStgPitch + j) * 4), "f"(v[16 * h + j]),
+                                     "f"(v[16 * h + j + 1]), "f"(v[16 * h + j + 2]), "f"(v[16 * h + j + 3])
+                                     : "memory");
+                    __syncwarp();
+                    const int cc = (lane & 3) * 4, col = n0 + c0 + 16 * h + cc;
+                    const int r_in = (lane >> 3) + 4 * ((lane >> 2) & 1);   // rows r and r+4 of a quarter-warp: distinct banks
+#pragma unroll
+                    for (int itr = 0; itr < 4; ++itr) {
+                        const int rr = itr * 8 + r_in;
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(stg + (rr * kStgPitch + cc) * 4));
+                        const int grow = row0 + rr;
+                        if (grow < p.M) {
+                            float* dst = cbase + (size_t)grow * p.ldc + col;
+                            if (vec_ok && col + 4 <= p.N) {
+                                *reinterpret_cast<float4*>(dst) = o;
+                            } else {
+                                if (col < p.N) dst[0] = o.x;
+                                if (col + 1 < p.N) dst[1] = o.y;
+                                if (col + 2 < p.N) dst[2] = o.z;
+                                if (col + 3 < p.N) dst[3] = o.w;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kAccumCols));
+    }
+}
+
+// C[m][n] = sum_s ws[s][m][n] (+ bias[n]), fixed order.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long mn, int N, const float* __restrict__ bias,
+                                     float* __restrict__ C, int ldc) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (long long)gridDim.x * blockDim.x) {
+        float acc = ws[i];
+        for (int s = 1; s < splits; ++s) acc += ws[(long long)s * mn + i];
+        const int n = (int)(i % N);
+        const long long m = i / N;
+        if (bias) acc += bias[n];
+        C[m * ldc + n] = acc;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// 2-D fp32 tensor [outer][ld] with `inner` valid contiguous elements per row; box = {box_inner (32 floats = 128 B), box_outer}.
+static bool make_map(CUtensorMap* map, const float* ptr, int inner, int outer, int ld, int box_inner, int box_outer, bool kmajor) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool A_K, bool B_K>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+    static size_t cache[kMaxDevices] = {};
+    auto kern = gemm3x_kernel<BN, A_K, B_K>;
+    cudaError_t e = ensure_dynamic_smem(kern, Cfg<BN>::kSmem, cache);
+    if (e != cudaSuccess) return (int)e;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int n_work = m_tiles * n_tiles * p.splits;
+    kern<<<n_work < kSMs ? n_work : kSMs, kThreads, Cfg<BN>::kSmem, stream>>>(ma, mb, p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int BN>
+static int launch_major(bool a_k, bool b_k, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
+    if (a_k) return b_k ? launch<BN, true, true>(ma, mb, p, st) : launch<BN, true, false>(ma, mb, p, st);
+    return b_k ? launch<BN, false, true>(ma, mb, p, st) : launch<BN, false, false>(ma, mb, p, st);
+}
+
+}  // namespace gemm
+}  // namespace spair
+
+using namespace spair;
+
+extern "C" int spair_gemm_block_n(int N, int b_kmajor) {
+    // the N tile: a divisor-friendly width for the decoder's G*G*(C+1) = 1568 = 7 * 224 columns, otherwise the widest tile
+    // whose padding waste stays small.  MN-major B tiles are built from 32-column swizzle atoms.
+    if (N % 224 == 0) return 224;
+    if (N > 128 && (N % 256 == 0 || N % 256 > 128)) return 256;
+    if (N > 64) return 128;
+    (void)b_kmajor;
+    return 64;
+}
+
+extern "C" int spair_gemm_splits(int M, int N, int K) {
+    const int bn = spair_gemm_block_n(N, 1);
+    const long long tiles = (long long)((M + gemm::BM - 1) / gemm::BM) * ((N + bn - 1) / bn);
+    if (tiles >= kSMs / 2 || K <= 4 * gemm::BK) return 1;
+    long long s = (2 * kSMs + tiles - 1) / tiles;          // about two work items per SM
+    const long long max_s = (K + 8 * gemm::BK - 1) / (8 * gemm::BK);   // at least 8 k-blocks per split
+    if (s > max_s) s = max_s;
+    return (int)(s < 1 ? 1 : s);
+}
+
+extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M,
+                            int N, int K, const float* bias, int epilogue, int period, float s_colour, float s_alpha, float b_alpha,
+                            float* workspace, int splits, void* stream) {
+    SPAIR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1);
+    SPAIR_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0);                                   // TMA: 16-byte row pitch
+    SPAIR_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0);
+    SPAIR_REQUIRE(epilogue >= SPAIR_GEMM_EPI_NONE && epilogue <= SPAIR_GEMM_EPI_TEXEL);
+    SPAIR_REQUIRE(epilogue != SPAIR_GEMM_EPI_TEXEL || period >= 2);
+    SPAIR_REQUIRE(splits == 1 || (workspace != nullptr && epilogue == SPAIR_GEMM_EPI_NONE));
+    const int bn = spair_gemm_block_n(N, b_kmajor);
+    CUtensorMap ma, mb;
+    bool ok = a_kmajor ? gemm::make_map(&ma, A, K, M, lda, gemm::BK, gemm::BM, true) : gemm::make_map(&ma, A, M, K, lda, 32, gemm::BK, false);
+    ok = ok && (b_kmajor ? gemm::make_map(&mb, B, K, N, ldb, gemm::BK, bn, true) : gemm::make_map(&mb, B, N, K, ldb, 32, gemm::BK, false));
+    SPAIR_REQUIRE(ok);
+    gemm::Params p;
+    p.M = M; p.N = N; p.K = K;
+    // the caller sizes the workspace for `splits`; the k-blocks are dealt out evenly and splits that would be empty are dropped
+    const int kb_total = (K + gemm::BK - 1) / gemm::BK;
+    const int kb_per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kb_per - 1) / kb_per;
+    p.splits = splits;
+    p.k_per_split = kb_per * gemm::BK;
+    p.C = splits == 1 ? C : workspace;
+    p.ldc = splits == 1 ? ldc : N;
+    p.bias = bias;
+    p.epilogue = epilogue;
+    p.period = period;
+    p.s_colour = s_colour; p.s_alpha = s_alpha; p.b_alpha = b_alpha;
+    const char* dbg = getenv("SPAIR_GEMM_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    switch (bn) {
+        case 224: rc = gemm::launch_major<224>(a_kmajor, b_kmajor, ma, mb, p, st); break;
+        case 256: rc = gemm::launch_major<256>(a_kmajor, b_kmajor, ma, mb, p, st); break;
+        case 128: rc = gemm::launch_major<128>(a_kmajor, b_kmajor, ma, mb, p, st); break;
+        default: rc = gemm::launch_major<64>(a_kmajor, b_kmajor, ma, mb, p, st); break;
+    }
+    if (rc != 0 || splits == 1) return rc;
+    const long long mn = (long long)M * N;
+    gemm::splitk_reduce_kernel<<<grid_for(mn, 256) < 4 * kSMs ? grid_for(mn, 256) : 4 * kSMs, 256, 0, st>>>(workspace, splits, mn, N, bias, C, ldc);
+    SPAIR_LAUNCH_CHECK();
+}

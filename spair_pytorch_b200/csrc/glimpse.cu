@@ -10,6 +10,8 @@
 // that do not fit the tile (only reachable through the generic stn() API) sample global memory
 // directly.  Backward wrt z_where is a per-object reduction (no atomics); the optional image
 // gradient (generic stn() API only — the model's image has no grad) is scattered with atomics.
+#include <stdlib.h>
+
 #include "warp_math.cuh"
 
 namespace spair {
@@ -207,6 +209,189 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
 }
 
 // ------------------------------------------------------------------------------------------
+// Image-resident variant (the model's path: many cells of the SAME image).  The per-object kernels above re-stage a
+// ~49x49 window per object — 3x more staged than sampled, plus the coordinate set-up of a whole CTA per object.  Here a
+// persistent CTA copies the whole image (C*Ih*Iw fp32 <= 96 KB: configs A and C) into shared memory with TMA bulk copies
+// behind an mbarrier and every warp extracts whole glimpses from it: the image is read from HBM/L2 once per CTA that
+// touches it, the only other traffic is the output (forward) / d_out (backward), written / read in 128-byte rows.
+// Work is split evenly over the grid in (image, cell) order, so a CTA loads at most two images.
+// ------------------------------------------------------------------------------------------
+constexpr int kResThreads = 256, kResWarps = kResThreads / 32;
+constexpr int kResMaxImageBytes = 96 * 1024;
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// whole image -> shared memory: bulk async copies (TMA, SASS UBLKCP) of <= 32 KB, completion counted on the mbarrier
+__device__ __forceinline__ void load_image_async(float* dst, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = min(32768u, bytes - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         g_smem_u32(dst) + off),
+                     "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(bar)
+                     : "memory");
+    }
+}
+
+struct ResArgs {
+    const float* image;
+    const float* z_where;
+    const int* cells;
+    int n_cells, B, HW, C, Ih, Iw, Gh, Gw;
+    float* out;            // forward: glimpses; backward: unused
+    const float* d_out;    // backward
+    float* d_zw;           // backward: [n_cells*B, 4]
+    int ld_out;
+    int per_cta;           // objects per CTA
+    float inv_Gw;
+};
+
+// per-warp tables of one object: column j -> {x0, x1 (clamped neighbour), wx0, wx1}; row i -> {y0*Iw, y1*Iw, wy0, wy1}.
+// The sample coordinate is clamped to [0, size-1] (padding_mode='border'); at the upper border the neighbour tap has weight
+// exactly 0, so reading the clamped texel instead of skipping the tap gives the same bits.
+__device__ __forceinline__ void res_tables(const FwdAffine& A, int Ih, int Iw, int Gh, int Gw, const float* base_x,
+                                           const float* base_y, float4* col, float4* row, float* col_m, float* row_m, int lane) {
+    for (int j = lane; j < Gw; j += 32) {
+        float ix = unnormalize(affine_coord(base_x[j], A.ax, A.cx), 0.5f * (float)Iw);
+        float m = 1.0f;
+        if (ix <= 0.0f) { ix = 0.0f; m = 0.0f; }
+        else if (ix >= (float)(Iw - 1)) { ix = (float)(Iw - 1); m = 0.0f; }
+        const float f0 = floorf(ix);
+        const int x0 = (int)f0;
+        col[j] = make_float4(__int_as_float(x0), __int_as_float(min(x0 + 1, Iw - 1)), f0 + 1.0f - ix, ix - f0);
+        if (col_m) col_m[j] = m;
+    }
+    for (int i = lane; i < Gh; i += 32) {
+        float iy = unnormalize(affine_coord(base_y[i], A.ay, A.cy), 0.5f * (float)Ih);
+        float m = 1.0f;
+        if (iy <= 0.0f) { iy = 0.0f; m = 0.0f; }
+        else if (iy >= (float)(Ih - 1)) { iy = (float)(Ih - 1); m = 0.0f; }
+        const float f0 = floorf(iy);
+        const int y0 = (int)f0;
+        row[i] = make_float4(__int_as_float(y0 * Iw), __int_as_float(min(y0 + 1, Ih - 1) * Iw), f0 + 1.0f - iy, iy - f0);
+        if (row_m) row_m[i] = m;
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kResThreads) glimpse_resident_kernel(ResArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int plane = p.Ih * p.Iw, img_floats = p.C * plane;
+    float* img = smem;
+    float* base_x = img + img_floats;
+    float* base_y = base_x + p.Gw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tab = p.Gw + p.Gh;
+    float4* tabs4 = reinterpret_cast<float4*>(smem + ((img_floats + tab + 3) & ~3));
+    float4* col = tabs4 + (size_t)warp * tab;
+    float4* row = col + p.Gw;
+    float* col_m = BWD ? reinterpret_cast<float*>(tabs4 + (size_t)kResWarps * tab) + (size_t)warp * tab : nullptr;   // clamp masks
+    float* row_m = BWD ? col_m + p.Gw : nullptr;
+    __shared__ __align__(8) uint64_t bar_storage;
+    const uint32_t bar = g_smem_u32(&bar_storage);
+
+    for (int j = threadIdx.x; j < p.Gw; j += kResThreads) base_x[j] = base_coord(j, p.Gw);
+    for (int i = threadIdx.x; i < p.Gh; i += kResThreads) base_y[i] = base_coord(i, p.Gh);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long total = (long long)p.B * p.n_cells;
+    const long long o0 = (long long)blockIdx.x * p.per_cta, o1 = min(total, o0 + p.per_cta);
+    const int GG = p.Gh * p.Gw;
+    uint32_t parity = 0;
+    for (int b = (int)(o0 / p.n_cells); (long long)b * p.n_cells < o1; ++b) {
+        const int k0 = (int)max(o0 - (long long)b * p.n_cells, 0LL), k1 = (int)min(o1 - (long long)b * p.n_cells, (long long)p.n_cells);
+        if (threadIdx.x == 0) load_image_async(img, p.image + (size_t)b * img_floats, (uint32_t)img_floats * 4u, bar);
+        g_mbar_wait(bar, parity);
+        parity ^= 1;
+        for (int k = k0 + warp; k < k1; k += kResWarps) {
+            const int cell = p.cells[k];
+            const long long r = (long long)k * p.B + b;                 // wavefront-major output row
+            const float4 zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + (size_t)b * p.HW + cell);
+            const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
+            res_tables(A, p.Ih, p.Iw, p.Gh, p.Gw, base_x, base_y, col, row, col_m, row_m, lane);
+            __syncwarp();
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int c = 0; c < p.C; ++c) {
+                const float* pl = img + (size_t)c * plane;
+                for (int t = lane; t < GG; t += 32) {
+                    const int i = fast_div(t, p.inv_Gw), j = t - i * p.Gw;
+                    const float4 cj = col[j], ri = row[i];
+                    const int x0 = __float_as_int(cj.x), x1 = __float_as_int(cj.y), y0 = __float_as_int(ri.x), y1 = __float_as_int(ri.y);
+                    const float v00 = pl[y0 + x0], v01 = pl[y0 + x1], v10 = pl[y1 + x0], v11 = pl[y1 + x1];
+                    if (!BWD) {
+                        float a = __fmul_rn(v00, __fmul_rn(cj.z, ri.z));
+                        a = fmaf(v01, __fmul_rn(cj.w, ri.z), a);
+                        a = fmaf(v10, __fmul_rn(cj.z, ri.w), a);
+                        a = fmaf(v11, __fmul_rn(cj.w, ri.w), a);
+                        p.out[r * p.ld_out + (size_t)c * GG + t] = a;
+                    } else {
+                        const float g = __ldg(p.d_out + r * p.ld_out + (size_t)c * GG + t);
+                        // grid_sampler_2d_backward: d out / d ix, d out / d iy; zero where the coordinate was clamped
+                        const float dgx = g * ((v01 - v00) * ri.z + (v11 - v10) * ri.w) * col_m[j];
+                        const float dgy = g * ((v10 - v00) * cj.z + (v11 - v01) * cj.w) * row_m[i];
+                        acc[0] += dgx;
+                        acc[1] += dgy;
+                        acc[2] = fmaf(dgx, base_x[j], acc[2]);
+                        acc[3] = fmaf(dgy, base_y[i], acc[3]);
+                    }
+                }
+            }
+            if (BWD) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+                if (lane == 0) {
+                    const float hx = 0.5f * (float)p.Iw, hy = 0.5f * (float)p.Ih;   // gx = xs * base + (2 xt - 1)
+                    *reinterpret_cast<float4*>(p.d_zw + r * 4) = make_float4(2.0f * hx * acc[0], 2.0f * hy * acc[1], hx * acc[2], hy * acc[3]);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();      // every warp is done with this image before the next bulk copy overwrites it
+    }
+}
+
+static size_t resident_smem(int C, int Ih, int Iw, int Gh, int Gw, bool bwd) {
+    const size_t head = ((size_t)C * Ih * Iw + Gw + Gh + 3) & ~(size_t)3;
+    return sizeof(float) * head + (size_t)kResWarps * (Gw + Gh) * (bwd ? 20 : 16);
+}
+
+// The resident path needs the model's call shape (cells of shared images), a TMA-copyable image and no image gradient.
+static bool resident_ok(const float* image, const int* cells, int C, int Ih, int Iw, int Gh, int Gw, const float* d_image) {
+    const size_t bytes = (size_t)C * Ih * Iw * 4;
+    return cells && !d_image && bytes <= (size_t)kResMaxImageBytes && bytes % 16 == 0 && ((uintptr_t)image % 16) == 0 &&
+           (long long)Gh * Gw < (1 << 15) && Gw <= 1024;
+}
+
+template <bool BWD>
+static int launch_resident(ResArgs a, cudaStream_t st) {
+    const size_t smem = resident_smem(a.C, a.Ih, a.Iw, a.Gh, a.Gw, BWD);
+    static size_t cache[kMaxDevices] = {};
+    cudaError_t e = ensure_dynamic_smem(glimpse_resident_kernel<BWD>, smem, cache);
+    if (e != cudaSuccess) return (int)e;
+    const long long total = (long long)a.B * a.n_cells;
+    const int ctas_per_sm = (int)((220 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((220 * 1024) / (smem + 1024));
+    long long per = (total + (long long)kSMs * ctas_per_sm - 1) / ((long long)kSMs * ctas_per_sm);
+    if (per < kResWarps) per = kResWarps;
+    a.per_cta = (int)per;
+    glimpse_resident_kernel<BWD><<<(unsigned)((total + per - 1) / per), kResThreads, smem, st>>>(a);
+    SPAIR_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // generic paste: stn(image, z_where, [Oh,Ow], inverse=True), zeros padding (modules.py:255-269)
 // ------------------------------------------------------------------------------------------
 __global__ void paste_fwd_kernel(const float* __restrict__ image, const float* __restrict__ z_where, int n, int C,
@@ -310,6 +495,10 @@ extern "C" int spair_glimpse_fwd(const float* image, const float* z_where, const
     SPAIR_REQUIRE(image && z_where && out && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
     SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
     SPAIR_REQUIRE(!cells || n_cells <= 65535);
+    if (resident_ok(image, cells, C, Ih, Iw, Gh, Gw, nullptr) && !getenv("SPAIR_GLIMPSE_PER_OBJECT")) {
+        ResArgs a{image, z_where, cells, n_cells, B, HW, C, Ih, Iw, Gh, Gw, out, nullptr, nullptr, ld_out, 0, 1.0f / (float)Gw};
+        return launch_resident<false>(a, (cudaStream_t)stream);
+    }
     const dim3 grid(B, cells ? n_cells : 1);
     const size_t smem = glimpse_smem(Gh, Gw, false);
     SPAIR_REQUIRE(smem <= 200 * 1024);
@@ -328,6 +517,10 @@ extern "C" int spair_glimpse_bwd(const float* image, const float* z_where, const
     SPAIR_REQUIRE(image && z_where && d_out && d_z_where_local && B > 0 && C > 0 && Ih > 1 && Iw > 1 && Gh > 0 && Gw > 0);
     SPAIR_REQUIRE(ld_out >= C * Gh * Gw && (!cells || n_cells > 0) && ((uintptr_t)z_where % 16) == 0);
     SPAIR_REQUIRE(!cells || n_cells <= 65535);
+    if (resident_ok(image, cells, C, Ih, Iw, Gh, Gw, d_image) && !getenv("SPAIR_GLIMPSE_PER_OBJECT")) {
+        ResArgs a{image, z_where, cells, n_cells, B, HW, C, Ih, Iw, Gh, Gw, nullptr, d_out, d_z_where_local, ld_out, 0, 1.0f / (float)Gw};
+        return launch_resident<true>(a, (cudaStream_t)stream);
+    }
     const dim3 grid(B, cells ? n_cells : 1);
     const size_t smem = glimpse_smem(Gh, Gw, true);
     SPAIR_REQUIRE(smem <= 200 * 1024);

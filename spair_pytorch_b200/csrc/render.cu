@@ -42,6 +42,7 @@ struct RenderArgs {
     const float* z_pres;
     int B, HW, G, Ih, Iw;
     float obj_scale, alpha_scale, alpha_bias;
+    int decoded;      // 1: `logits` holds texel records already through the sigmoids (spair_gemm3x, SPAIR_GEMM_EPI_TEXEL)
     float* recon;
     float* denom;
     const float* target;
@@ -62,12 +63,23 @@ struct Tex {
 __device__ __forceinline__ float sigmoid_analytical(float x) { return __fdividef(1.0f, __expf(-x) + 1.0f); }
 
 // decode one texel: colours, alpha (with presence), importance  (models.py:485-500)
+// `decoded`: l already holds sigma(obj_scale * logit) per colour channel and 1 - sigma(alpha_scale * logit + alpha_bias) for the
+// alpha channel (the complement keeps sigma'(x) = s (1 - s) accurate where the +5 bias saturates alpha), written by the
+// decoder GEMM's epilogue; only the per-object factors remain.
 template <int C>
 __device__ __forceinline__ void decode_texel(const float* __restrict__ l, float obj_scale, float alpha_scale,
-                                             float alpha_bias, float pres, float depth, float* out) {
+                                             float alpha_bias, float pres, float depth, int decoded, float* out) {
+    float s;
+    if (decoded) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[c] = sigmoid_analytical(__fmul_rn(l[c], obj_scale));
-    const float a = sigmoid_analytical(__fadd_rn(__fmul_rn(l[C], alpha_scale), alpha_bias)) * pres;
+        for (int c = 0; c < C; ++c) out[c] = l[c];
+        s = 1.0f - l[C];
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = sigmoid_analytical(__fmul_rn(l[c], obj_scale));
+        s = sigmoid_analytical(__fadd_rn(__fmul_rn(l[C], alpha_scale), alpha_bias));
+    }
+    const float a = s * pres;
     out[C] = a;
     out[C + 1] = fmaxf(__fmul_rn(a, depth), 0.01f);
 }
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
                 Tex<C> o;
 #pragma unroll
                 for (int i = 0; i < NF4 * 4; ++i) o.v[i] = 0.0f;
-                decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, o.v);
+                decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, p.decoded, o.v);
 #pragma unroll
                 for (int q = 0; q < NF4; ++q)
                     slot[(size_t)tex * NF4 + q] = make_float4(o.v[4 * q], o.v[4 * q + 1], o.v[4 * q + 2], o.v[4 * q + 3]);
@@ -317,6 +329,7 @@ struct RenderBwdArgs {
     const float* z_pres;
     int B, HW, G, Ih, Iw;
     float obj_scale, alpha_scale, alpha_bias;
+    int decoded;
     const float* gs;
     float* d_logits;
     float* d_z_where;
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kRThreads, (C <= 2) ? 4 : 3) render_bwd_kernel
         if (yp >= 1 && yp <= G && xp >= 1 && xp <= G) {
             float l[C + 1];
             load_logits<C>(lbase + (size_t)((yp - 1) * G + xp - 1) * (C + 1), l);
-            decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, o.v);
+            decode_texel<C>(l, p.obj_scale, p.alpha_scale, p.alpha_bias, pres, depth, p.decoded, o.v);
         }
 #pragma unroll
         for (int q = 0; q < NF4; ++q) tex[(size_t)t * NF4 + q] = make_float4(o.v[4 * q], o.v[4 * q + 1], o.v[4 * q + 2], o.v[4 * q + 3]);
@@ -540,12 +553,25 @@ __global__ void __launch_bounds__(kRThreads, (C <= 2) ? 4 : 3) render_bwd_kernel
         float dl[C + 1];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float e = __expf(-__fmul_rn(l[c], p.obj_scale));
-            const float s = __fdividef(1.0f, e + 1.0f);
-            dl[c] = dT[q][c] * e * s * s * p.obj_scale;
+            float ds;   // sigma'(x) = e s^2 = s (1 - s)
+            if (p.decoded) {
+                ds = l[c] * (1.0f - l[c]);
+            } else {
+                const float e = __expf(-__fmul_rn(l[c], p.obj_scale));
+                const float s = __fdividef(1.0f, e + 1.0f);
+                ds = e * s * s;
+            }
+            dl[c] = dT[q][c] * ds * p.obj_scale;
         }
-        const float e = __expf(-__fadd_rn(__fmul_rn(l[C], p.alpha_scale), p.alpha_bias));
-        const float s = __fdividef(1.0f, e + 1.0f);
+        float s, ds;
+        if (p.decoded) {
+            s = 1.0f - l[C];
+            ds = s * l[C];
+        } else {
+            const float e = __expf(-__fadd_rn(__fmul_rn(l[C], p.alpha_scale), p.alpha_bias));
+            s = __fdividef(1.0f, e + 1.0f);
+            ds = e * s * s;
+        }
         const float a = s * pres;
         float d_a = dT[q][C];
         if (__fmul_rn(a, depth) >= 0.01f) {                                  // clamp(min=0.01) passes the gradient (models.py:500)
@@ -553,7 +579,7 @@ __global__ void __launch_bounds__(kRThreads, (C <= 2) ? 4 : 3) render_bwd_kernel
             acc[4] = fmaf(dT[q][C + 1], a, acc[4]);
         }
         acc[5] = fmaf(d_a, s, acc[5]);                                       // alpha = sigmoid * z_pres (models.py:496)
-        dl[C] = d_a * pres * e * s * s * p.alpha_scale;
+        dl[C] = d_a * pres * ds * p.alpha_scale;
         if (C == 1) {
             *reinterpret_cast<float2*>(dl_base + (size_t)t * 2) = make_float2(dl[0], dl[1]);
         } else if (C == 3) {
@@ -624,13 +650,13 @@ extern "C" int spair_render_num_tiles(int B, int Ih, int Iw) {
 
 extern "C" int spair_render_fwd(const float* logits, const float* z_where, const float* z_depth, const float* z_pres,
                                 int B, int HW, int C, int G, int Ih, int Iw, float obj_scale, float alpha_scale,
-                                float alpha_bias, float* recon, float* denom, const float* target, float* bce_partial,
-                                void* stream) {
+                                float alpha_bias, int decoded, float* recon, float* denom, const float* target,
+                                float* bce_partial, void* stream) {
     SPAIR_REQUIRE(logits && z_where && z_depth && z_pres && recon);
     SPAIR_REQUIRE(B > 0 && B <= 65535 && HW > 0 && HW <= 65535 && G > 0 && G * G <= 1024 && Ih > 0 && Iw > 0);
     SPAIR_REQUIRE((target == nullptr) == (bce_partial == nullptr));
     SPAIR_REQUIRE(((uintptr_t)z_where % 16) == 0 && ((uintptr_t)logits % 16) == 0);
-    RenderArgs a{logits, z_where, z_depth, z_pres, B, HW, G, Ih, Iw, obj_scale, alpha_scale, alpha_bias,
+    RenderArgs a{logits, z_where, z_depth, z_pres, B, HW, G, Ih, Iw, obj_scale, alpha_scale, alpha_bias, decoded,
                  recon, denom, target, bce_partial, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
@@ -644,14 +670,14 @@ extern "C" int spair_render_fwd(const float* logits, const float* z_where, const
 
 extern "C" int spair_render_bwd(const float* logits, const float* z_where, const float* z_depth, const float* z_pres,
                                 int B, int HW, int C, int G, int Ih, int Iw, float obj_scale, float alpha_scale,
-                                float alpha_bias, const float* recon, const float* denom, const float* d_recon,
+                                float alpha_bias, int decoded, const float* recon, const float* denom, const float* d_recon,
                                 const float* target, const float* bce_scale, float* gs_ws, float* d_logits,
                                 float* d_z_where, float* d_z_depth, float* d_z_pres, void* stream) {
     SPAIR_REQUIRE(logits && z_where && z_depth && z_pres && recon && denom && gs_ws);
     SPAIR_REQUIRE(d_logits && d_z_where && d_z_depth && d_z_pres && (d_recon || target));
     SPAIR_REQUIRE(B > 0 && HW > 0 && G > 0 && G * G <= 1024 && Ih > 0 && Iw > 0);
     SPAIR_REQUIRE(((uintptr_t)z_where % 16) == 0 && ((uintptr_t)logits % 16) == 0 && ((uintptr_t)d_logits % 16) == 0);
-    RenderBwdArgs a{logits, z_where, z_depth, z_pres, B, HW, G, Ih, Iw, obj_scale, alpha_scale, alpha_bias,
+    RenderBwdArgs a{logits, z_where, z_depth, z_pres, B, HW, G, Ih, Iw, obj_scale, alpha_scale, alpha_bias, decoded,
                     gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres};
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {

@@ -77,8 +77,8 @@ _SIGNATURES = {
     "spair_paste_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_paste_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "spair_render_num_tiles": [_I, _I, _I],
-    "spair_render_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P],
-    "spair_render_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "spair_render_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P, _P],
+    "spair_render_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "spair_kl_fwd": [_P] * 6 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
@@ -86,6 +86,9 @@ _SIGNATURES = {
     "spair_stem_conv_fwd": [_P, _P, _P] + [_I] * 11 + [_P, _P],
     "spair_stem_conv_bwd": [_P, _P, _P] + [_I] * 11 + [_P, _P, _P, _P],
     "spair_broadcast_rows": [_P, _I, _I, _P, _P],
+    "spair_gemm_block_n": [_I, _I],
+    "spair_gemm_splits": [_I, _I, _I],
+    "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
@@ -96,7 +99,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 RENDER_MAX_TEXELS, RENDER_MAX_CHANNELS = 1024, 4   # spair_render_fwd/bwd: G*G <= 1024, C <= 4 (csrc/render.cu)
 MAX_NEIGHBOURS = 12   # SPAIR_MAX_NEIGHBOURS of include/spair_b200.h (N_LOOKBACK <= 2)
-ABI_VERSION = 2       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
+ABI_VERSION = 3       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
 
 
 def lib() -> ctypes.CDLL:
@@ -353,6 +356,47 @@ def stem_conv_bwd(x, y, dy, w_shape, stride: int, pad_t: int, pad_l: int, ws, d_
 
 
 # ----------------------------------------------------------------------------------------
+# tcgen05 3xTF32 GEMM (csrc/gemm.cu)
+# ----------------------------------------------------------------------------------------
+GEMM_EPI_NONE, GEMM_EPI_RELU, GEMM_EPI_TEXEL = 0, 1, 2
+_GEMM_WS = {}
+
+
+def gemm_supported(*mats) -> bool:
+    """TMA needs 16-byte aligned rows: every operand a 2-D fp32 view with unit column stride and a row pitch that is a
+    multiple of 4 floats."""
+    return all(t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in mats)
+
+
+def _gemm_workspace(device, floats):
+    """Split-K partial products: one growing buffer per (device, stream) so that GEMMs forked to side streams never share it."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _GEMM_WS.get(key)
+    if ws is None or ws.numel() < floats:
+        ws = torch.empty(floats, device=device, dtype=torch.float32)
+        _GEMM_WS[key] = ws
+    return ws
+
+
+def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, period=2, scales=(1.0, 1.0, 0.0), splits=None):
+    """out[M,N] = op(A) . op(B) (+ bias) on the tensor cores at fp32 accuracy (see spair_gemm3x in include/spair_b200.h).
+    a_kmajor: A is [M,K] (else [K,M]); b_kmajor: B is [N,K] (else [K,N])."""
+    M, N = out.shape
+    Kd = A.shape[1] if a_kmajor else A.shape[0]
+    assert (A.shape[0] if a_kmajor else A.shape[1]) == M and (B.shape[0] if b_kmajor else B.shape[1]) == N
+    assert (B.shape[1] if b_kmajor else B.shape[0]) == Kd
+    if splits is None:
+        splits = lib().spair_gemm_splits(M, N, Kd) if epilogue == GEMM_EPI_NONE else 1
+    ws = _gemm_workspace(out.device, splits * M * N) if splits > 1 else None
+    _check(lib().spair_gemm3x(_ptr(A), _ld(A), int(a_kmajor), _ptr(B), _ld(B), int(b_kmajor), _ptr(out), _ld(out), M, N, Kd,
+                              _ptr(bias), epilogue, period, float(scales[0]), float(scales[1]), float(scales[2]), _ptr(ws),
+                              splits, _stream()), "spair_gemm3x")
+    if splits > 1:
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1      # the fixed-order split-K reduction
+
+
+# ----------------------------------------------------------------------------------------
 # fused forward sweep
 # ----------------------------------------------------------------------------------------
 def sweep_max_rows() -> int:
@@ -390,7 +434,7 @@ def sweep_mlp_desc(packed, first, biases, X, H0, H1, Y) -> SweepMLP:
     for i, b in enumerate(biases):
         m.wt[i], m.b[i] = _ptr(packed.fwd[first + i]), _ptr(_contig(b, "bias"))
         m.n[i], m.k[i] = packed.shapes[first + i]
-    m.x, m.ld_x, m.h0, m.h1, m.y = _ptr(_contig(X, "X")), X.shape[1], _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), \
+    m.x, m.ld_x, m.h0, m.h1, m.y = _ptr(X, "X"), _ld(X), _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), \
         _ptr(_contig(Y, "Y"))
     return m
 
@@ -414,7 +458,7 @@ def sweep_mlp_bwd_desc(packed, first, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBw
         m.w[i] = _ptr(packed.bwd[first + i])
         m.n[i], m.k[i] = packed.shapes[first + i]
     m.h0, m.h1, m.y = _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), _ptr(_contig(Y, "Y"))
-    m.dx, m.ld_dx = _ptr(_contig(dX, "dX")), dX.shape[1]
+    m.dx, m.ld_dx = _ptr(dX, "dX"), _ld(dX)
     m.dh0, m.dh1, m.dy = _ptr(_contig(dH0, "dH0")), _ptr(_contig(dH1, "dH1")), _ptr(_contig(dY, "dY"))
     return m
 
@@ -470,19 +514,19 @@ def render_num_tiles(B, Ih, Iw):
     return lib().spair_render_num_tiles(B, Ih, Iw)
 
 
-def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, bce_partial):
+def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, bce_partial, decoded=False):
     _check(lib().spair_render_fwd(_ptr(_contig(logits, "logits")), _ptr(_contig(z_where, "z_where")),
                                   _ptr(_contig(z_depth, "z_depth")), _ptr(_contig(z_pres, "z_pres")), B, HW, C, G, Ih, Iw,
-                                  float(scales[0]), float(scales[1]), float(scales[2]), _ptr(_contig(recon, "recon")),
+                                  float(scales[0]), float(scales[1]), float(scales[2]), int(decoded), _ptr(_contig(recon, "recon")),
                                   _ptr(_contig(denom, "denom")), _ptr(_contig(target, "target")),
                                   _ptr(_contig(bce_partial, "bce_partial")), _stream()), "spair_render_fwd")
 
 
 def render_bwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, d_recon, target, bce_scale,
-               gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres):
+               gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres, decoded=False):
     _check(lib().spair_render_bwd(_ptr(_contig(logits, "logits")), _ptr(_contig(z_where, "z_where")),
                                   _ptr(_contig(z_depth, "z_depth")), _ptr(_contig(z_pres, "z_pres")), B, HW, C, G, Ih, Iw,
-                                  float(scales[0]), float(scales[1]), float(scales[2]), _ptr(recon), _ptr(denom),
+                                  float(scales[0]), float(scales[1]), float(scales[2]), int(decoded), _ptr(recon), _ptr(denom),
                                   _ptr(_contig(d_recon, "d_recon")), _ptr(_contig(target, "target")), _ptr(bce_scale),
                                   _ptr(gs_ws), _ptr(_contig(d_logits, "d_logits")), _ptr(_contig(d_z_where, "d_z_where")),
                                   _ptr(_contig(d_z_depth, "d_z_depth")), _ptr(_contig(d_z_pres, "d_z_pres")), _stream()),
@@ -510,6 +554,6 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
 # device guard on every launch wrapper (see _device_guarded)
 for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
               "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
-              "sweep_bwd", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+              "sweep_bwd", "gemm3x", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
     globals()[_name] = _device_guarded(globals()[_name])
 del _name

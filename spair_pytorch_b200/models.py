@@ -234,10 +234,18 @@ class SPAIR(nn.Module):
 
         # decoder MLP over all N = B*HW objects at once (reference models.py:474-481), cuBLAS
         dec = self.object_decoder
-        hidden = dec[:-1](attr.reshape(B * HW, c.n_attr))
-        logits = ops.WideLinearFunction.apply(hidden, dec[-1].weight, dec[-1].bias)
+        linears = [m for m in dec if isinstance(m, nn.Linear)]
+        decoded = ops.USE_TENSOR_CORE_GEMM and len(linears) == 3 and linears[1].in_features % 4 == 0 \
+            and linears[2].in_features % 4 == 0
+        if decoded:
+            # tcgen05 GEMMs; the last one writes sigmoid-decoded texel records instead of logits (ops.DecoderFunction)
+            logits = ops.DecoderFunction.apply(attr.reshape(B * HW, c.n_attr), *(p for m in linears for p in (m.weight, m.bias)),
+                                               C + 1, c.scales)
+        else:
+            hidden = dec[:-1](attr.reshape(B * HW, c.n_attr))
+            logits = ops.WideLinearFunction.apply(hidden, dec[-1].weight, dec[-1].bias)
         recon_x, recon_loss, _ = ops.RenderFunction.apply(logits, z_where.reshape(B * HW, 4), depth.reshape(-1),
-                                                          pres.reshape(-1), x, B, HW, C, plan.G, Ih, Iw, c.scales)
+                                                          pres.reshape(-1), x, B, HW, C, plan.G, Ih, Iw, c.scales, decoded)
         kl_sums, kl_map = ops.KLFunction.apply(dmean, dstd, pres, plan.prior_mean, plan.prior_std, count_dist0, c.n_attr)
         kl_means = kl_sums.mean(dim=0)                       # batch mean of per-image sums (models.py:553)
         loss = recon_loss + (c.beta * self.kl_scale) * kl_means.sum()   # models.py:558

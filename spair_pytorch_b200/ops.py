@@ -28,6 +28,11 @@ from .schedule import WavefrontSchedule
 # stream: {"fwd": (start, end), "bwd": (start, end)}.  None (the default) records nothing.
 SWEEP_EVENTS: Optional[dict] = None
 
+# SPAIR_NO_TC_GEMM=1 keeps the decoder and the weight gradients on cuBLAS fp32 (the round-1 path; for A/B timing and as the
+# reference the tensor-core path is tested against)
+import os as _os
+USE_TENSOR_CORE_GEMM = "SPAIR_NO_TC_GEMM" not in _os.environ
+
 
 def _timed_launch(name, fn, *args):
     if SWEEP_EVENTS is None:
@@ -41,6 +46,22 @@ def _timed_launch(name, fn, *args):
 
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.contiguous()
+
+
+def _rows16(rows: int, width: int, device, zero=False) -> torch.Tensor:
+    """[rows, width] fp32 view whose row pitch is a multiple of 4 floats (16 bytes), the unit TMA addresses rows in."""
+    pitch = (width + 3) & ~3
+    buf = (torch.zeros if zero else torch.empty)(rows, pitch, device=device, dtype=torch.float32)
+    return buf if pitch == width else buf[:, :width]
+
+
+def _tma_rows(t: torch.Tensor) -> torch.Tensor:
+    """``t`` itself when the tcgen05 GEMM can load it (K.gemm_supported), else a copy with a 16-byte row pitch."""
+    if K.gemm_supported(t):
+        return t
+    out = _rows16(t.shape[0], t.shape[1], t.device)
+    out.copy_(t)
+    return out
 
 
 # ==========================================================================================
@@ -101,7 +122,10 @@ class RenderFunction(torch.autograd.Function):
     -> (recon [B,C,Ih,Iw], bce_sum scalar).  N = B*HW, objects of one image contiguous."""
 
     @staticmethod
-    def forward(ctx, logits, z_where, z_depth, z_pres, target, B, HW, C, G, Ih, Iw, scales):
+    def forward(ctx, logits, z_where, z_depth, z_pres, target, B, HW, C, G, Ih, Iw, scales, decoded=False):
+        """``decoded``: ``logits`` are the texel records of ``DecoderFunction`` (already through the sigmoids).  The
+        gradient returned for them is then the gradient wrt the RAW logits (the sigmoid derivative is applied here from
+        the records, where it costs nothing), which is what ``DecoderFunction.backward`` expects."""
         logits, z_where, z_depth, z_pres = _c(logits), _c(z_where), _c(z_depth), _c(z_pres)
         dev = logits.device
         recon = torch.empty(B, C, Ih, Iw, device=dev, dtype=torch.float32)
@@ -110,10 +134,10 @@ class RenderFunction(torch.autograd.Function):
         if target is not None:
             target = _c(target)
             partial = torch.empty(K.render_num_tiles(B, Ih, Iw), device=dev, dtype=torch.float32)
-        K.render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, partial)
+        K.render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, partial, decoded)
         bce = partial.sum() if partial is not None else torch.zeros((), device=dev)
         ctx.save_for_backward(logits, z_where, z_depth, z_pres, recon, denom, target)
-        ctx.meta = (B, HW, C, G, Ih, Iw, scales)
+        ctx.meta = (B, HW, C, G, Ih, Iw, scales, decoded)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(denom)
         return recon, bce, denom
@@ -121,10 +145,10 @@ class RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_recon, d_bce, _d_denom):
         logits, z_where, z_depth, z_pres, recon, denom, target = ctx.saved_tensors
-        B, HW, C, G, Ih, Iw, scales = ctx.meta
+        B, HW, C, G, Ih, Iw, scales, decoded = ctx.meta
         dev = logits.device
         if d_bce is None and d_recon is None:
-            return (None,) * 12
+            return (None,) * 13
         use_target = target if d_bce is not None else None
         bce_scale = _c(d_bce.reshape(1).float()) if d_bce is not None else None
         gs = torch.empty(B, C + 1, Ih, Iw, device=dev, dtype=torch.float32)
@@ -133,8 +157,8 @@ class RenderFunction(torch.autograd.Function):
         d_depth = torch.empty_like(z_depth)
         d_pres = torch.empty_like(z_pres)
         K.render_bwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, _c(d_recon), use_target,
-                     bce_scale, gs, d_logits, d_zw, d_depth, d_pres)
-        return (d_logits, d_zw, d_depth, d_pres) + (None,) * 8
+                     bce_scale, gs, d_logits, d_zw, d_depth, d_pres, decoded)
+        return (d_logits, d_zw, d_depth, d_pres) + (None,) * 9
 
 
 # ==========================================================================================
@@ -226,7 +250,7 @@ class _ManualMLP:
         self.W, self.b = weights, biases
         self.widths = [w.shape[0] for w in weights]
         self.n_in = weights[0].shape[1]
-        self.X = torch.empty(rows, self.n_in, device=device, dtype=torch.float32)
+        self.X = _rows16(rows, self.n_in, device)          # 16-byte row pitch: the weight-gradient GEMM loads it with TMA
         self.H = [torch.empty(rows, w, device=device, dtype=torch.float32) for w in self.widths[:-1]]
         self.Y = torch.empty(rows, self.widths[-1], device=device, dtype=torch.float32)
         self.dX = self.dH = self.dY = None
@@ -240,7 +264,7 @@ class _ManualMLP:
         torch.addmm(self.b[-1], inp, self.W[-1].t(), out=self.Y[r0:r1])
 
     def alloc_grads(self):
-        self.dX = torch.empty_like(self.X)
+        self.dX = _rows16(self.X.shape[0], self.n_in, self.X.device)
         self.dH = [torch.empty_like(h) for h in self.H]
         self.dY = torch.empty_like(self.Y)
 
@@ -263,9 +287,70 @@ class _ManualMLP:
         inputs = [self.X] + self.H
         grads = self.dH + [self.dY]
         for g, i, dW, db in zip(grads, inputs, self.dW, self.db):
-            torch.mm(g.t(), i, out=dW)
+            if USE_TENSOR_CORE_GEMM:
+                # dW[n_out, n_in] = g^T i, both operands MN-major as stored (a head output of 102 or 1 columns is first
+                # copied to a 16-byte row pitch: 12 MB, against a 30976-row reduction)
+                K.gemm3x(_tma_rows(g), False, _tma_rows(i), False, dW)
+            else:
+                torch.mm(g.t(), i, out=dW)
             torch.sum(g, 0, out=db)
         return self.dW, self.db
+
+
+class DecoderFunction(torch.autograd.Function):
+    """``object_decoder`` (reference models.py:165,474-481: Linear(A,128) ReLU Linear(128,256) ReLU Linear(256, G*G*(C+1)))
+    followed by the per-texel sigmoids of SPAIR._render (models.py:485-493), for all N = B*HW objects at once.
+
+    The two wide layers run on the tcgen05 GEMM of csrc/gemm.cu (3xTF32, fp32 accuracy); the last one applies
+    bias + scale + sigmoid in its epilogue, so the [N, G*G*(C+1)] logits (194 MB at the default config) never reach HBM:
+    the output is the texel records ``RenderFunction(decoded=True)`` consumes.  Backward takes the gradient wrt the RAW
+    logits (that is what ``RenderFunction.backward`` returns in decoded mode) and runs dgrad / wgrad on the same kernel.
+    The first layer (K = A = 50: rows are not 16-byte multiples, so no TMA) is 3 % of the FLOPs and stays on cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, attr, w0, b0, w1, b1, w2, b2, period, scales):
+        attr = _c(attr)
+        w0, b0, w1, b1, w2, b2 = (t.detach().contiguous() for t in (w0, b0, w1, b1, w2, b2))
+        n, dev = attr.shape[0], attr.device
+        # K = A = 50 columns are 200-byte rows: zero-padded copies with a 16-byte pitch (6 MB) put this layer on TMA too
+        attr_p = _rows16(n, attr.shape[1], dev, zero=True)
+        attr_p.copy_(attr)
+        w0_p = _rows16(w0.shape[0], w0.shape[1], dev, zero=True)
+        w0_p.copy_(w0)
+        h0 = torch.empty(n, w0.shape[0], device=dev, dtype=torch.float32)
+        K.gemm3x(attr_p, True, w0_p, True, h0, b0, epilogue=K.GEMM_EPI_RELU)
+        h1 = torch.empty(n, w1.shape[0], device=dev, dtype=torch.float32)
+        K.gemm3x(h0, True, w1, True, h1, b1, epilogue=K.GEMM_EPI_RELU)
+        texels = torch.empty(n, w2.shape[0], device=dev, dtype=torch.float32)
+        K.gemm3x(h1, True, w2, True, texels, b2, epilogue=K.GEMM_EPI_TEXEL, period=period, scales=scales)
+        ctx.save_for_backward(attr_p, h0, h1, w0_p, w1, w2)
+        return texels
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        attr, h0, h1, w0, w1, w2 = ctx.saved_tensors
+        d_logits = _c(d_logits)
+        n, dev = attr.shape[0], attr.device
+        d_w2 = torch.empty_like(w2)
+        K.gemm3x(d_logits, False, h1, False, d_w2)
+        d_b2 = d_logits.sum(0)
+        d_h1 = torch.empty_like(h1)
+        K.gemm3x(d_logits, True, w2, False, d_h1)
+        K.relu_bwd(d_h1, h1)
+        d_w1 = torch.empty_like(w1)
+        K.gemm3x(d_h1, False, h0, False, d_w1)
+        d_b1 = d_h1.sum(0)
+        d_h0 = torch.empty_like(h0)
+        K.gemm3x(d_h1, True, w1, False, d_h0)
+        K.relu_bwd(d_h0, h0)
+        d_w0 = torch.empty_like(w0)
+        K.gemm3x(d_h0, False, attr, False, d_w0)
+        d_b0 = d_h0.sum(0)
+        d_attr = None
+        if ctx.needs_input_grad[0]:
+            d_attr = torch.empty_like(attr)
+            K.gemm3x(d_h0, True, w0, False, d_attr)
+        return d_attr, d_w0, d_b0, d_w1, d_b1, d_w2, d_b2, None, None
 
 
 class WideLinearFunction(torch.autograd.Function):

@@ -23,6 +23,10 @@ def install(monkeypatch):
         if callable(fn) and hasattr(K, name) and not name.startswith("_") and name not in ("install",):
             monkeypatch.setattr(K, name, fn)
     monkeypatch.setattr(K, "require_cuda", lambda *a, **k: None)
+    # the tcgen05 GEMM path (decoder texel records, gemm3x weight gradients) has no test double: host-logic tests run
+    # the cuBLAS-shaped branch of ops.py / models.py; the GPU tests cover both branches
+    from spair_pytorch_b200 import ops
+    monkeypatch.setattr(ops, "USE_TENSOR_CORE_GEMM", False)
 
 
 def parallel_branches(device, stream_pool, thunks):
@@ -272,7 +276,8 @@ def _render(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales):
     return torch.clamp((img * (imp_w / S)).sum(dim=1), min=0, max=1), S[:, 0, 0]
 
 
-def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, bce_partial):
+def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, target, bce_partial, decoded=False):
+    assert not decoded
     r, S = _render(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales)
     recon[:] = r
     if denom is not None:
@@ -283,7 +288,8 @@ def render_fwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, re
 
 @torch.enable_grad()
 def render_bwd(logits, z_where, z_depth, z_pres, B, HW, C, G, Ih, Iw, scales, recon, denom, d_recon, target, bce_scale,
-               gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres):
+               gs_ws, d_logits, d_z_where, d_z_depth, d_z_pres, decoded=False):
+    assert not decoded
     leaves = [t.detach().clone().requires_grad_(True) for t in (logits, z_where, z_depth, z_pres)]
     r, _ = _render(*leaves, B, HW, C, G, Ih, Iw, scales)
     total = 0

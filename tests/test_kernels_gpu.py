@@ -90,10 +90,15 @@ def test_paste_matches_reference_golden():
     assert_close(z.grad, g["g45/inv_d_z_where"], "d z_where", atol=1e-5 + 1e-4 * float(np.abs(g["g45/inv_d_z_where"]).max()))
 
 
-@pytest.mark.parametrize("C,I,G,B,Hc", [(1, 128, 28, 4, 11), (3, 64, 14, 3, 8), (1, 40, 8, 2, 5), (2, 50, 7, 2, 4)])
-def test_glimpse_wavefront_rows_vs_oracle(C, I, G, B, Hc):
+@pytest.mark.parametrize("per_object", [False, True], ids=["image-resident", "per-object"])
+@pytest.mark.parametrize("C,I,G,B,Hc", [(1, 128, 28, 4, 11), (3, 64, 14, 3, 8), (1, 40, 8, 2, 5), (2, 50, 7, 2, 4), (1, 36, 40, 2, 3), (1, 37, 12, 2, 3)])
+def test_glimpse_wavefront_rows_vs_oracle(C, I, G, B, Hc, per_object, monkeypatch):
     """Wavefront addressing (row r = k*B + b samples image b with z_where[b, cells[k]]), forward and
-    the z_where gradient; includes boxes hanging over the border and I % 4 != 0 (non-staged path)."""
+    the z_where gradient; includes boxes hanging over the border and I % 4 != 0 (non-staged path).  Both schedules of
+    csrc/glimpse.cu: the image-resident kernel (whole image in shared memory by TMA bulk copy, a warp per glimpse) and the
+    per-object kernel it replaces on this call shape (kept for images that do not fit and for the generic stn() API)."""
+    if per_object:
+        monkeypatch.setenv("SPAIR_GLIMPSE_PER_OBJECT", "1")
     HW = Hc * Hc
     rs = gen(C * 100 + I)
     image = torch.rand(B, C, I, I, generator=rs)

@@ -13,6 +13,11 @@ DEV = "cuda"
 # measured budgets (profiles/r02_parity_escapes.json); see OTHER_SHAPES
 ESCAPE_BUDGET_A32 = 0.0
 ESCAPE_BUDGET_A2500 = 0.5
+# config D, B=1: the weight gradients now come from the 3xTF32 tensor-core GEMM (csrc/gemm.cu), whose rounding differs from
+# the fp32 reference's by ~1e-6 of sum|a||b|.  Measured: 2 of the 2,266,987 checked gradient elements (both in
+# box_network.body.dense0.weight, 32,400 elements) sit just outside (rtol, atol) of the fp32 reference and inside it of the
+# float64 evaluation; no ref_err / kink escapes.  Budget: 1e-4 of a tensor's elements.
+ESCAPE_BUDGET_D1 = 1e-4
 
 
 @pytest.mark.parametrize("fused", [(True, True), (True, False), (False, False)],
@@ -44,7 +49,7 @@ def _run_oracle(net, x, step, noise, name):
 # criterion.  ("A", 32, 1001) is BASELINE.json configs[0] as written: spair/config.py defaults, batch 32 (reference
 # train.py:48-66 with cfg.BATCH_SIZE = 32).  Where the budget is non-zero the reference's own fp32 backward is rounding noise
 # on those tensors and the counts are written to profiles/r02_parity_escapes.json.
-OTHER_SHAPES = [("C", 2, 1001, 0.0), ("rgb64", 2, 1001, 0.0), ("D", 1, 1001, 0.0), ("tiny_lb2", 3, 1001, 0.0),
+OTHER_SHAPES = [("C", 2, 1001, 0.0), ("rgb64", 2, 1001, 0.0), ("D", 1, 1001, ESCAPE_BUDGET_D1), ("tiny_lb2", 3, 1001, 0.0),
                 ("A", 32, 1001, ESCAPE_BUDGET_A32), ("A", 3, 2500, ESCAPE_BUDGET_A2500)]
 
 
@@ -84,7 +89,7 @@ def test_model_vs_oracle_other_shapes(name, B, step, budget):
     assert not failures, "\n".join(failures)
     case = "oracle %s B=%d step %d" % (name, B, step)
     helpers.record_escapes(case, report)
-    helpers.assert_no_escapes(report, case, max_fraction=budget, min_cos=(1.0 - 1e-6) if budget == 0.0 else 0.999)
+    helpers.assert_no_escapes(report, case, max_fraction=budget, min_cos=(1.0 - 1e-6) if budget <= 1e-4 else 0.999)
 
 
 def test_full_size_config_B_properties():
