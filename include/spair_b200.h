@@ -373,7 +373,22 @@ int spair_gemm_block_n(int N, int b_kmajor);
 int spair_gemm_splits(int M, int N, int K);
 int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M,
                  int N, int K, const float* bias /* [N] or NULL */, int epilogue, int period, float s_colour, float s_alpha,
-                 float b_alpha, float* workspace, int splits, void* stream);
+                 float b_alpha, float* workspace, int splits,
+                 unsigned* kink_ws, int kink_cap /* SPAIR_GEMM_EPI_RELU with both operands K-major: outputs whose
+                     pre-activation is within the product's rounding error of zero are listed in kink_ws ([0] = counter,
+                     then up to kink_cap entries) and re-evaluated with float64 accumulation by a second launch, so that
+                     the ReLU takes the exact branch (the reference's gradient below the layer depends on it); NULL / 0: off */,
+                 void* stream);
+
+/* Patch gather / transposed gather around spair_gemm3x for the k x k / stride s convolutions of the backbone tail
+ * (reference modules.py:44-66), channels-last activations.  col[m][(kh*k + kw)*C + c] = x[b][s*oy+kh][s*ox+kw][c] with
+ * m = (b*Ho + oy)*Wo + ox, Ho = (H-k)/s + 1 (no padding: the Backbone pads once, before the stem);
+ * spair_col2im_nhwc is its adjoint (dx[b][y][x][c] = sum of the d_col entries that read x[b][y][x][c], fixed order).
+ * C must be a multiple of 4; x / col / dx 16-byte aligned. */
+int spair_im2col_nhwc(const float* x /* [B,H,W,C] */, int B, int H, int W, int C, int k, int stride,
+                      float* col /* [B*Ho*Wo, k*k*C] */, void* stream);
+int spair_col2im_nhwc(const float* dcol /* [B*Ho*Wo, k*k*C] */, int B, int H, int W, int C, int k, int stride,
+                      float* dx /* [B,H,W,C] */, void* stream);
 
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);

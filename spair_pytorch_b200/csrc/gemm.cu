@@ -114,7 +114,16 @@ struct Params {
     int period;           // texel decode: channels per texel (C + 1)
     float s_colour, s_alpha, b_alpha;
     int debug;            // diagnostics (SPAIR_GEMM_DEBUG): 1 = splitters skip their work, 2 = one MMA per k-step, 4 = no stores
+    int acc_split;        // 1, or 4 (BN <= 128): k-block j accumulates into TMEM accumulator j % 4, summed in the epilogue
+    unsigned* kink_ws;    // ReLU sign fix-up list: [0] = counter, [1 .. kink_cap] = row * N + col of uncertain outputs
+    int kink_cap;
 };
+
+// A ReLU output whose pre-activation is within the GEMM's own rounding error of zero may take the other branch than the
+// fp32 reference does; the gradient of every layer below then differs by ~1/sqrt(#activations) (a "kink").  Outputs with
+// |v| < kKinkTol * (largest |v| of the 32 neighbouring columns) are therefore listed and re-evaluated by
+// relu_fixup_kernel with float64 accumulation, so the sign decision is the exact one.
+constexpr float kKinkTol = 4.8828125e-4f;   // 2^-11: > 30x the measured worst-case error of a K = 2048 reduction
 
 template <int BN>
 struct Cfg {
@@ -229,12 +238,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 int mt, nt, sp;
                 decode(w, mt, nt, sp);
                 const int kb_n = k_blocks_of(sp);
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                // The tensor core adds every MMA into the fp32 accumulator with truncation, so the error of a long reduction
+                // grows with the number of accumulations.  acc_split = 4 deals the k-blocks over four accumulators (the whole
+                // TMEM, no double buffering) and the epilogue sums them with round-to-nearest adds: ~8x smaller error,
+                // used for the K = 2048 forward convolutions whose ReLU decisions the reference's gradients depend on.
+                const bool split4 = p.acc_split == 4;
+                const int acc = split4 ? 0 : (it & 1);
+                const uint32_t acc_phase = split4 ? (it & 1) : ((it >> 1) & 1);
                 mbar_wait(bar_acc_empty(acc), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + acc * kAccumCols;
                 for (int kb = 0; kb < kb_n; ++kb) {
+                    const uint32_t d = tmem_base + (split4 ? (kb & 3) * 128 : acc * kAccumCols);
+                    const int first = split4 ? (kb < 4) : (kb == 0);
                     mbar_wait(bar_ready(stage), phase);
                     tc_fence_after();
 #pragma unroll
@@ -244,11 +259,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const uint64_t dbh = smem_desc(b_hi(stage) + kk * b_step, b_lbo, b_sbo, b_lay);
                         const uint64_t dbl = smem_desc(b_lo(stage) + kk * b_step, b_lbo, b_sbo, b_lay);
                         if (!(p.debug & 2)) {
-                            umma_tf32(d, dal, dbh, idesc, (kb | kk) != 0);
+                            umma_tf32(d, dal, dbh, idesc, !(first && kk == 0));
                             umma_tf32(d, dah, dbl, idesc, 1);
                             umma_tf32(d, dah, dbh, idesc, 1);
                         } else {
-                            umma_tf32(d, dah, dbh, idesc, (kb | kk) != 0);
+                            umma_tf32(d, dah, dbh, idesc, !(first && kk == 0));
                         }
                     }
                     umma_commit(bar_empty(stage));   // the stage may be refilled once these MMAs have read it
@@ -302,8 +317,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             int mt, nt, sp;
             decode(w, mt, nt, sp);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const bool split4 = p.acc_split == 4;
+            const int acc = split4 ? 0 : (it & 1);
+            const uint32_t acc_phase = split4 ? (it & 1) : ((it >> 1) & 1);
+            const int n_acc = split4 ? min(4, k_blocks_of(sp)) : 1;
             mbar_wait(bar_acc_full(acc), acc_phase);
             tc_fence_after();
             const int row0 = mt * BM + q * 32;
@@ -315,10 +332,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccumCols + c0, r);
-                if (n0 + c0 >= p.N || (p.debug & 4)) continue;   // warp-uniform
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int a = 1; a < n_acc; ++a) {      // acc_split: the other accumulators of this tile (128 columns apart)
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 128 + c0, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                if (n0 + c0 >= p.N || (p.debug & 4)) continue;   // warp-uniform
                 if (p.splits == 1) {
                     if (p.bias) {
 #pragma unroll
@@ -326,6 +348,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                             if (n0 + c0 + j < p.N) v[j] += __ldg(p.bias + n0 + c0 + j);
                     }
                     if (p.epilogue == SPAIR_GEMM_EPI_RELU) {
+                        if (p.kink_ws && row0 + lane < p.M) {
+                            float vmax = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, fabsf(v[j]));
+                            const float tol = vmax * kKinkTol;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (fabsf(v[j]) <= tol && n0 + c0 + j < p.N) {
+                                    const unsigned slot = atomicAdd(p.kink_ws, 1u);
+                                    if (slot < (unsigned)p.kink_cap) p.kink_ws[1 + slot] = (unsigned)(row0 + lane) * (unsigned)p.N + (unsigned)(n0 + c0 + j);
+                                }
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
                     } else if (p.epilogue == SPAIR_GEMM_EPI_TEXEL) {
@@ -389,6 +424,30 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kAccumCols));
+    }
+}
+
+// One warp per listed output: v = sum_k A[m][k] B[n][k] + bias[n] accumulated in float64 (exact to ~1e-16 relative, so the
+// sign is the true one), C[m][n] = max(v, 0).  K-major operands only (the forward layers).
+__global__ void __launch_bounds__(256) relu_fixup_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                         const float* __restrict__ bias, float* __restrict__ C, int ldc, int N, int K,
+                                                         const unsigned* __restrict__ kink_ws, int cap) {
+    const unsigned count = min(kink_ws[0], (unsigned)cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
+        const unsigned idx = kink_ws[1 + e];
+        const unsigned m = idx / (unsigned)N, n = idx - m * (unsigned)N;
+        const float* a = A + (size_t)m * lda;
+        const float* b = B + (size_t)n * ldb;
+        double acc = 0.0;
+        for (int k = lane; k < K; k += 32) acc += (double)a[k] * (double)b[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            if (bias) acc += (double)bias[n];
+            C[(size_t)m * ldc + n] = acc > 0.0 ? (float)acc : 0.0f;
+        }
     }
 }
 
@@ -478,7 +537,7 @@ extern "C" int spair_gemm_splits(int M, int N, int K) {
 
 extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M,
                             int N, int K, const float* bias, int epilogue, int period, float s_colour, float s_alpha, float b_alpha,
-                            float* workspace, int splits, void* stream) {
+                            float* workspace, int splits, unsigned* kink_ws, int kink_cap, void* stream) {
     SPAIR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1);
     SPAIR_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0);                                   // TMA: 16-byte row pitch
     SPAIR_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0);
@@ -504,15 +563,29 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
     p.epilogue = epilogue;
     p.period = period;
     p.s_colour = s_colour; p.s_alpha = s_alpha; p.b_alpha = b_alpha;
+    // forward layers with a long reduction whose ReLU decisions matter: split accumulators (see the MMA warp)
+    p.acc_split = (epilogue == SPAIR_GEMM_EPI_RELU && bn <= 128 && splits == 1 && K >= 512) ? 4 : 1;
+    const bool fixup = kink_ws != nullptr && kink_cap > 0 && epilogue == SPAIR_GEMM_EPI_RELU;
+    SPAIR_REQUIRE(!fixup || (a_kmajor && b_kmajor && splits == 1 && (long long)M * N < (1ll << 32)));
+    p.kink_ws = fixup ? kink_ws : nullptr;
+    p.kink_cap = kink_cap;
     const char* dbg = getenv("SPAIR_GEMM_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (fixup) {
+        cudaError_t e = cudaMemsetAsync(kink_ws, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     int rc;
     switch (bn) {
         case 224: rc = gemm::launch_major<224>(a_kmajor, b_kmajor, ma, mb, p, st); break;
         case 256: rc = gemm::launch_major<256>(a_kmajor, b_kmajor, ma, mb, p, st); break;
         case 128: rc = gemm::launch_major<128>(a_kmajor, b_kmajor, ma, mb, p, st); break;
         default: rc = gemm::launch_major<64>(a_kmajor, b_kmajor, ma, mb, p, st); break;
+    }
+    if (rc == 0 && fixup) {
+        gemm::relu_fixup_kernel<<<2 * kSMs, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, N, K, kink_ws, kink_cap);
+        SPAIR_LAUNCH_CHECK();
     }
     if (rc != 0 || splits == 1) return rc;
     const long long mn = (long long)M * N;

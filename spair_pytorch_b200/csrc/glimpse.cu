@@ -216,7 +216,7 @@ glimpse_bwd_kernel(const float* __restrict__ image, const float* __restrict__ z_
 // touches it, the only other traffic is the output (forward) / d_out (backward), written / read in 128-byte rows.
 // Work is split evenly over the grid in (image, cell) order, so a CTA loads at most two images.
 // ------------------------------------------------------------------------------------------
-constexpr int kResThreads = 256, kResWarps = kResThreads / 32;
+constexpr int kResThreads = 384, kResWarps = kResThreads / 32;   // 3 CTAs x 12 warps per SM at a 64 KB image
 constexpr int kResMaxImageBytes = 96 * 1024;
 
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -256,47 +256,36 @@ struct ResArgs {
     float inv_Gw;
 };
 
-// per-warp tables of one object: column j -> {x0, x1 (clamped neighbour), wx0, wx1}; row i -> {y0*Iw, y1*Iw, wy0, wy1}.
-// The sample coordinate is clamped to [0, size-1] (padding_mode='border'); at the upper border the neighbour tap has weight
-// exactly 0, so reading the clamped texel instead of skipping the tap gives the same bits.
-__device__ __forceinline__ void res_tables(const FwdAffine& A, int Ih, int Iw, int Gh, int Gw, const float* base_x,
-                                           const float* base_y, float4* col, float4* row, float* col_m, float* row_m, int lane) {
-    for (int j = lane; j < Gw; j += 32) {
-        float ix = unnormalize(affine_coord(base_x[j], A.ax, A.cx), 0.5f * (float)Iw);
-        float m = 1.0f;
-        if (ix <= 0.0f) { ix = 0.0f; m = 0.0f; }
-        else if (ix >= (float)(Iw - 1)) { ix = (float)(Iw - 1); m = 0.0f; }
-        const float f0 = floorf(ix);
-        const int x0 = (int)f0;
-        col[j] = make_float4(__int_as_float(x0), __int_as_float(min(x0 + 1, Iw - 1)), f0 + 1.0f - ix, ix - f0);
-        if (col_m) col_m[j] = m;
-    }
-    for (int i = lane; i < Gh; i += 32) {
-        float iy = unnormalize(affine_coord(base_y[i], A.ay, A.cy), 0.5f * (float)Ih);
-        float m = 1.0f;
-        if (iy <= 0.0f) { iy = 0.0f; m = 0.0f; }
-        else if (iy >= (float)(Ih - 1)) { iy = (float)(Ih - 1); m = 0.0f; }
-        const float f0 = floorf(iy);
-        const int y0 = (int)f0;
-        row[i] = make_float4(__int_as_float(y0 * Iw), __int_as_float(min(y0 + 1, Ih - 1) * Iw), f0 + 1.0f - iy, iy - f0);
-        if (row_m) row_m[i] = m;
-    }
+// One axis of an object's sampling grid at glimpse index `base` (normalised coordinate): {first tap offset, second tap offset
+// (clamped neighbour), weight of the first tap, weight of the second} with offsets pre-multiplied by `pitch`, and the
+// clip mask of grid_sampler's clip_coordinates_set_grad.  The sample coordinate is clamped to [0, size-1]
+// (padding_mode='border'); at the upper border the neighbour tap has weight exactly 0, so reading the clamped texel
+// instead of skipping the tap gives the same bits.
+__device__ __forceinline__ float4 res_axis(float base, float a, float c, int size, int pitch, float& mask) {
+    float ix = unnormalize(affine_coord(base, a, c), 0.5f * (float)size);
+    mask = 1.0f;
+    if (ix <= 0.0f) { ix = 0.0f; mask = 0.0f; }
+    else if (ix >= (float)(size - 1)) { ix = (float)(size - 1); mask = 0.0f; }
+    const float f0 = floorf(ix);
+    const int x0 = (int)f0;
+    return make_float4(__int_as_float(x0 * pitch), __int_as_float(min(x0 + 1, size - 1) * pitch), f0 + 1.0f - ix, ix - f0);
 }
 
+// Thread mapping: a lane owns ONE glimpse column j for the whole kernel (its taps' x offsets and weights stay in registers
+// per object) and the warp walks the glimpse rows, 32 / Gw of them per iteration (28 of 32 lanes busy at Gw = 28 or 14);
+// the row entry is a broadcast shared-memory read.  Per texel that leaves the four gathers from the resident image, four
+// weight products, the interpolation and one coalesced store (forward) or load (backward).  Gw > 32: columns in chunks of 32.
 template <bool BWD>
-__global__ void __launch_bounds__(kResThreads) glimpse_resident_kernel(ResArgs p) {
+__global__ void __launch_bounds__(kResThreads, 3) glimpse_resident_kernel(ResArgs p) {
     extern __shared__ __align__(16) float smem[];
     const int plane = p.Ih * p.Iw, img_floats = p.C * plane;
     float* img = smem;
     float* base_x = img + img_floats;
     float* base_y = base_x + p.Gw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tab = p.Gw + p.Gh;
-    float4* tabs4 = reinterpret_cast<float4*>(smem + ((img_floats + tab + 3) & ~3));
-    float4* col = tabs4 + (size_t)warp * tab;
-    float4* row = col + p.Gw;
-    float* col_m = BWD ? reinterpret_cast<float*>(tabs4 + (size_t)kResWarps * tab) + (size_t)warp * tab : nullptr;   // clamp masks
-    float* row_m = BWD ? col_m + p.Gw : nullptr;
+    float4* rows4 = reinterpret_cast<float4*>(smem + ((img_floats + p.Gw + p.Gh + 3) & ~3));
+    float4* row = rows4 + (size_t)warp * p.Gh;
+    float* row_m = BWD ? reinterpret_cast<float*>(rows4 + (size_t)kResWarps * p.Gh) + (size_t)warp * p.Gh : nullptr;   // clamp masks
     __shared__ __align__(8) uint64_t bar_storage;
     const uint32_t bar = g_smem_u32(&bar_storage);
 
@@ -307,6 +296,12 @@ __global__ void __launch_bounds__(kResThreads) glimpse_resident_kernel(ResArgs p
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // lane -> (row within an iteration, column); constant for the whole kernel
+    const int rpi = p.Gw <= 32 ? fast_div(32, p.inv_Gw) : 1;          // glimpse rows per warp iteration
+    const int sub = p.Gw <= 32 ? fast_div(lane, p.inv_Gw) : 0;
+    const int j_lane = p.Gw <= 32 ? lane - sub * p.Gw : lane;
+    const bool lane_on = sub < rpi;
 
     const long long total = (long long)p.B * p.n_cells;
     const long long o0 = (long long)blockIdx.x * p.per_cta, o1 = min(total, o0 + p.per_cta);
@@ -322,31 +317,44 @@ __global__ void __launch_bounds__(kResThreads) glimpse_resident_kernel(ResArgs p
             const long long r = (long long)k * p.B + b;                 // wavefront-major output row
             const float4 zw = __ldg(reinterpret_cast<const float4*>(p.z_where) + (size_t)b * p.HW + cell);
             const FwdAffine A(zw.x, zw.y, zw.z, zw.w);
-            res_tables(A, p.Ih, p.Iw, p.Gh, p.Gw, base_x, base_y, col, row, col_m, row_m, lane);
+            for (int i = lane; i < p.Gh; i += 32) {
+                float m;
+                row[i] = res_axis(base_y[i], A.ay, A.cy, p.Ih, p.Iw, m);
+                if (BWD) row_m[i] = m;
+            }
             __syncwarp();
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            for (int c = 0; c < p.C; ++c) {
-                const float* pl = img + (size_t)c * plane;
-                for (int t = lane; t < GG; t += 32) {
-                    const int i = fast_div(t, p.inv_Gw), j = t - i * p.Gw;
-                    const float4 cj = col[j], ri = row[i];
-                    const int x0 = __float_as_int(cj.x), x1 = __float_as_int(cj.y), y0 = __float_as_int(ri.x), y1 = __float_as_int(ri.y);
-                    const float v00 = pl[y0 + x0], v01 = pl[y0 + x1], v10 = pl[y1 + x0], v11 = pl[y1 + x1];
-                    if (!BWD) {
-                        float a = __fmul_rn(v00, __fmul_rn(cj.z, ri.z));
-                        a = fmaf(v01, __fmul_rn(cj.w, ri.z), a);
-                        a = fmaf(v10, __fmul_rn(cj.z, ri.w), a);
-                        a = fmaf(v11, __fmul_rn(cj.w, ri.w), a);
-                        p.out[r * p.ld_out + (size_t)c * GG + t] = a;
-                    } else {
-                        const float g = __ldg(p.d_out + r * p.ld_out + (size_t)c * GG + t);
-                        // grid_sampler_2d_backward: d out / d ix, d out / d iy; zero where the coordinate was clamped
-                        const float dgx = g * ((v01 - v00) * ri.z + (v11 - v10) * ri.w) * col_m[j];
-                        const float dgy = g * ((v10 - v00) * cj.z + (v11 - v01) * cj.w) * row_m[i];
-                        acc[0] += dgx;
-                        acc[1] += dgy;
-                        acc[2] = fmaf(dgx, base_x[j], acc[2]);
-                        acc[3] = fmaf(dgy, base_y[i], acc[3]);
+            for (int j = j_lane; j < p.Gw; j += 32) {
+                float col_m;
+                const float bx = base_x[j];
+                const float4 cj = res_axis(bx, A.ax, A.cx, p.Iw, 1, col_m);
+                const int x0 = __float_as_int(cj.x), x1 = __float_as_int(cj.y);
+                for (int c = 0; c < p.C; ++c) {
+                    const float* pl = img + (size_t)c * plane;
+                    const size_t o_base = r * p.ld_out + (size_t)c * GG + j;
+                    if (!lane_on) continue;
+#pragma unroll 7
+                    for (int i = sub; i < p.Gh; i += rpi) {
+                        float g = 0.0f;
+                        if (BWD) g = __ldg(p.d_out + o_base + (size_t)i * p.Gw);      // issued first: the HBM latency to hide
+                        const float4 ri = row[i];
+                        const int y0 = __float_as_int(ri.x), y1 = __float_as_int(ri.y);
+                        const float v00 = pl[y0 + x0], v01 = pl[y0 + x1], v10 = pl[y1 + x0], v11 = pl[y1 + x1];
+                        if (!BWD) {
+                            float a = __fmul_rn(v00, __fmul_rn(cj.z, ri.z));
+                            a = fmaf(v01, __fmul_rn(cj.w, ri.z), a);
+                            a = fmaf(v10, __fmul_rn(cj.z, ri.w), a);
+                            a = fmaf(v11, __fmul_rn(cj.w, ri.w), a);
+                            p.out[o_base + (size_t)i * p.Gw] = a;
+                        } else {
+                            // grid_sampler_2d_backward: d out / d ix, d out / d iy; zero where the coordinate was clamped
+                            const float dgx = g * ((v01 - v00) * ri.z + (v11 - v10) * ri.w) * col_m;
+                            const float dgy = g * ((v10 - v00) * cj.z + (v11 - v01) * cj.w) * row_m[i];
+                            acc[0] += dgx;
+                            acc[1] += dgy;
+                            acc[2] = fmaf(dgx, bx, acc[2]);
+                            acc[3] = fmaf(dgy, base_y[i], acc[3]);
+                        }
                     }
                 }
             }
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(kResThreads) glimpse_resident_kernel(ResArgs p
 
 static size_t resident_smem(int C, int Ih, int Iw, int Gh, int Gw, bool bwd) {
     const size_t head = ((size_t)C * Ih * Iw + Gw + Gh + 3) & ~(size_t)3;
-    return sizeof(float) * head + (size_t)kResWarps * (Gw + Gh) * (bwd ? 20 : 16);
+    return sizeof(float) * head + (size_t)kResWarps * Gh * (bwd ? 20 : 16);
 }
 
 // The resident path needs the model's call shape (cells of shared images), a TMA-copyable image and no image gradient.

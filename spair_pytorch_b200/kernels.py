@@ -88,7 +88,9 @@ _SIGNATURES = {
     "spair_broadcast_rows": [_P, _I, _I, _P, _P],
     "spair_gemm_block_n": [_I, _I],
     "spair_gemm_splits": [_I, _I, _I],
-    "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P],
+    "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P],
+    "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
@@ -98,6 +100,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
 RENDER_MAX_TEXELS, RENDER_MAX_CHANNELS = 1024, 4   # spair_render_fwd/bwd: G*G <= 1024, C <= 4 (csrc/render.cu)
+NUM_SMS = 148          # kSMs of csrc/common.cuh (B200: 2 dies x 74 SMs)
 MAX_NEIGHBOURS = 12   # SPAIR_MAX_NEIGHBOURS of include/spair_b200.h (N_LOOKBACK <= 2)
 ABI_VERSION = 3       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
 
@@ -378,9 +381,24 @@ def _gemm_workspace(device, floats):
     return ws
 
 
-def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, period=2, scales=(1.0, 1.0, 0.0), splits=None):
+_KINK_WS = {}
+KINK_CAP = 1 << 20     # entries of the ReLU sign fix-up list (4 MB); overflowing entries simply keep the 3xTF32 value
+
+
+def _kink_workspace(device):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _KINK_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(1 + KINK_CAP, device=device, dtype=torch.int32)
+        _KINK_WS[key] = ws
+    return ws
+
+
+def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, period=2, scales=(1.0, 1.0, 0.0), splits=None,
+           exact_relu=True):
     """out[M,N] = op(A) . op(B) (+ bias) on the tensor cores at fp32 accuracy (see spair_gemm3x in include/spair_b200.h).
-    a_kmajor: A is [M,K] (else [K,M]); b_kmajor: B is [N,K] (else [K,N])."""
+    a_kmajor: A is [M,K] (else [K,M]); b_kmajor: B is [N,K] (else [K,N]).  ``exact_relu``: with the ReLU epilogue, outputs
+    within rounding error of the kink are re-evaluated in float64 (two launches instead of one)."""
     M, N = out.shape
     Kd = A.shape[1] if a_kmajor else A.shape[0]
     assert (A.shape[0] if a_kmajor else A.shape[1]) == M and (B.shape[0] if b_kmajor else B.shape[1]) == N
@@ -388,12 +406,28 @@ def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, per
     if splits is None:
         splits = lib().spair_gemm_splits(M, N, Kd) if epilogue == GEMM_EPI_NONE else 1
     ws = _gemm_workspace(out.device, splits * M * N) if splits > 1 else None
+    fix = exact_relu and epilogue == GEMM_EPI_RELU and a_kmajor and b_kmajor and splits == 1 and M * N < (1 << 32)
+    kink = _kink_workspace(out.device) if fix else None
     _check(lib().spair_gemm3x(_ptr(A), _ld(A), int(a_kmajor), _ptr(B), _ld(B), int(b_kmajor), _ptr(out), _ld(out), M, N, Kd,
                               _ptr(bias), epilogue, period, float(scales[0]), float(scales[1]), float(scales[2]), _ptr(ws),
-                              splits, _stream()), "spair_gemm3x")
-    if splits > 1:
+                              splits, kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _stream()), "spair_gemm3x")
+    if splits > 1 or fix:
         global LAUNCH_COUNT
-        LAUNCH_COUNT += 1      # the fixed-order split-K reduction
+        LAUNCH_COUNT += 1      # the fixed-order split-K reduction / the ReLU sign fix-up
+
+
+def im2col_nhwc(x, k: int, stride: int, col):
+    """x [B,H,W,C] channels-last -> col [B*Ho*Wo, k*k*C] (see spair_im2col_nhwc)."""
+    B, H, W, C = x.shape
+    _check(lib().spair_im2col_nhwc(_ptr(_contig(x, "x")), B, H, W, C, k, stride, _ptr(_contig(col, "col")), _stream()),
+           "spair_im2col_nhwc")
+
+
+def col2im_nhwc(dcol, k: int, stride: int, dx):
+    """Adjoint of im2col_nhwc: d_col [B*Ho*Wo, k*k*C] -> dx [B,H,W,C]."""
+    B, H, W, C = dx.shape
+    _check(lib().spair_col2im_nhwc(_ptr(_contig(dcol, "dcol")), B, H, W, C, k, stride, _ptr(_contig(dx, "dx")), _stream()),
+           "spair_col2im_nhwc")
 
 
 # ----------------------------------------------------------------------------------------
@@ -554,6 +588,6 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
 # device guard on every launch wrapper (see _device_guarded)
 for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
               "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
-              "sweep_bwd", "gemm3x", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+              "sweep_bwd", "gemm3x", "im2col_nhwc", "col2im_nhwc", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
     globals()[_name] = _device_guarded(globals()[_name])
 del _name

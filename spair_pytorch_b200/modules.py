@@ -103,9 +103,35 @@ class Backbone(Module):
             return None
         return ops.StemConvFunction.apply(x, conv.weight, conv.bias, stride, pt, pl, Ho, Wo)
 
+    def _gemm_tail(self, y):
+        """conv_1 .. conv_out on the tcgen05 GEMM (ops.ConvTailFunction) when every layer has the shape it covers;
+        None otherwise (cuDNN)."""
+        from . import ops
+        layers = list(self.net)[2:]
+        if not (ops.USE_TENSOR_CORE_GEMM and y.is_cuda and y.dtype == torch.float32):
+            return None
+        specs, params, i, cin = [], [], 0, y.shape[1]
+        while i < len(layers):
+            conv = layers[i]
+            if not (isinstance(conv, Conv2d) and conv.padding == (0, 0) and conv.dilation == (1, 1) and conv.groups == 1
+                    and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
+                    and conv.bias is not None and conv.in_channels == cin and cin % 4 == 0):
+                return None
+            relu = i + 1 < len(layers) and isinstance(layers[i + 1], ReLU)
+            if i + 1 < len(layers) and not relu:
+                return None
+            specs.append((conv.kernel_size[0], conv.stride[0], relu))
+            params += [conv.weight, conv.bias]
+            cin = conv.out_channels
+            i += 2 if relu else 1
+        return ops.ConvTailFunction.apply(y, tuple(specs), *params) if specs else None
+
     def forward(self, x):
         y = self._fused_stem(x)
         if y is not None:
+            tail = self._gemm_tail(y)
+            if tail is not None:
+                return tail
             for layer in list(self.net)[2:]:
                 y = layer(y)
             return y

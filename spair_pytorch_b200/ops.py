@@ -400,6 +400,73 @@ class StemConvFunction(torch.autograd.Function):
         return None, d_w, d_b, None, None, None, None, None
 
 
+class ConvTailFunction(torch.autograd.Function):
+    """The backbone after the stem (reference modules.py:44-66: [Conv2d(k, stride) + ReLU]* + a 1x1 ``conv_out`` without
+    activation) as GEMMs on the tcgen05 kernel of csrc/gemm.cu, forward and backward.
+
+    cuDNN has no fp32-accurate tensor-core convolution (TF32 is off for parity), so the library path runs these layers
+    on the fp32 SIMT / FFT engines at ~20 TFLOP/s — 8 of the 16.4 ms of a config-B step.  Here the activations are kept
+    channels-last, a 1x1 layer is a GEMM on the stored tensor, a k x k / stride s layer a GEMM on its patch matrix
+    (csrc/conv.cu), bias + ReLU run in the GEMM epilogue, and the backward is dgrad / wgrad on the same kernel plus the
+    transposed patch gather.  Layers: padding 0, dilation 1, groups 1, square kernel, Cin % 4 == 0.
+
+    forward(y0 [B,C0,H0,W0] NCHW (the stem's output), specs, *weights_and_biases) -> feat [B,F,Hc,Wc] NCHW;
+    ``specs`` = ((k, stride, relu), ...)."""
+
+    @staticmethod
+    def forward(ctx, y0, specs, *params):
+        x = y0.permute(0, 2, 3, 1).contiguous()                     # channels-last from here on
+        saved, shapes = [], []
+        for li, (k, s, relu) in enumerate(specs):
+            w, b = params[2 * li].detach(), params[2 * li + 1].detach().contiguous()
+            Bn, H, W, Cin = x.shape
+            Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+            M = Bn * Ho * Wo
+            wr = w.permute(0, 2, 3, 1).reshape(w.shape[0], k * k * Cin).contiguous()     # [Cout, (kh, kw, c)]
+            if k == 1 and s == 1:
+                a = x.view(M, Cin)
+            else:
+                a = torch.empty(M, k * k * Cin, device=x.device, dtype=torch.float32)
+                K.im2col_nhwc(x, k, s, a)
+            y = torch.empty(M, w.shape[0], device=x.device, dtype=torch.float32)
+            K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
+            saved += [a, wr, y]
+            shapes.append((Bn, H, W, Cin, Ho, Wo, tuple(w.shape)))
+            x = y.view(Bn, Ho, Wo, w.shape[0])
+        ctx.save_for_backward(*saved)
+        ctx.specs, ctx.shapes = specs, shapes
+        return x.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_feat):
+        specs, shapes, saved = ctx.specs, ctx.shapes, ctx.saved_tensors
+        Bn, _, _, _, Ho, Wo, wshape = shapes[-1]
+        dy = d_feat.permute(0, 2, 3, 1).reshape(Bn * Ho * Wo, wshape[0]).contiguous()
+        grads = [None] * (2 * len(specs))
+        for li in range(len(specs) - 1, -1, -1):
+            k, s, relu = specs[li]
+            a, wr, y = saved[3 * li: 3 * li + 3]
+            Bn, H, W, Cin, Ho, Wo, wshape = shapes[li]
+            if relu:
+                K.relu_bwd(dy, y)
+            d_wr = torch.empty_like(wr)
+            K.gemm3x(dy, False, a, False, d_wr)
+            grads[2 * li] = d_wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2).contiguous()
+            grads[2 * li + 1] = dy.sum(0)
+            if li == 0 and not ctx.needs_input_grad[0]:
+                return (None, None) + tuple(grads)
+            da = torch.empty_like(a)
+            K.gemm3x(dy, True, wr, False, da)
+            if k == 1 and s == 1:
+                dy = da
+            else:
+                dx = torch.empty(Bn, H, W, Cin, device=da.device, dtype=torch.float32)
+                K.col2im_nhwc(da, k, s, dx)
+                dy = dx.view(Bn * H * W, Cin)
+        Bn, H, W, Cin = shapes[0][:4]
+        return (dy.view(Bn, H, W, Cin).permute(0, 3, 1, 2).contiguous(), None) + tuple(grads)
+
+
 class CellSweepFunction(torch.autograd.Function):
     """forward(plan, x, feat, edge, eps_where, eps_attr, eps_depth, u_pres, wheel, *params)
     -> (z_where [B,HW,4], attr [B,HW,A], depth [B,HW], pres [B,HW], dmean [B,HW,D], dstd [B,HW,D], box [B,HW,4])
@@ -457,7 +524,9 @@ class CellSweepFunction(torch.autograd.Function):
                  and A + 6 <= 64 and len(s.offsets) <= K.MAX_NEIGHBOURS)
         if fused:
             # ONE persistent launch: a CTA owns `ipc` images and walks all wavefronts (csrc/sweep.cu)
-            ipc = max(1, min(2, max_rows // s.max_cells))
+            # images per CTA: two share one pass over the weight stream when there are more images than SMs; below that
+            # (strong scaling: 64-128 images per GPU) one image per CTA keeps twice as many SMs busy
+            ipc = max(1, min(2, max_rows // s.max_cells)) if B > K.NUM_SMS else 1
             dims = K.SweepDims(B=B, HW=HW, Hc=s.Hc, Wc=s.Wc, F=F, A=A, P=P, C=plan.C, Ih=plan.Ih, Iw=plan.Iw, G=G, ipc=ipc,
                                n_wavefronts=s.n_wavefronts, max_cells=s.max_cells, n_nb=len(s.offsets))
             packed = K.PackedSweepWeights([w for m in mlps for w in m.W])   # both layouts, one launch; kept for backward

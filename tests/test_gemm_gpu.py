@@ -4,6 +4,8 @@ Checker: torch fp64 on the same inputs (the reference's `nn.Linear` / autograd a
 models.py:474-493).  Bar: rtol 1e-4 / atol 1e-5 in fp32 (north_star); the split-precision product is measured against
 the fp64 result relative to sum_k |a||b| — fp32 cuBLAS sits at ~3e-7 on that scale, 3xTF32 must stay below 5e-6.
 """
+import copy
+
 import pytest
 import torch
 
@@ -133,3 +135,71 @@ def test_decoder_function_matches_cublas_path():
         rel = float((a - b).double().norm() / (b.double().norm() + 1e-30))
         assert rel < 1e-4, (i, rel)
         assert_close(a, b, "grad %d" % i, atol=1e-5 + 1e-4 * float(b.abs().max()))
+
+
+@pytest.mark.parametrize("shape,topology", [((1, 96, 96), None), ((3, 64, 64), "cell8")])
+def test_conv_tail_matches_cudnn(shape, topology, monkeypatch):
+    """Backbone tail (conv_1 .. conv_out, reference modules.py:44-66) on the tcgen05 GEMM + patch gather (ops.ConvTailFunction,
+    csrc/conv.cu) against the cuDNN fp32 path of the same module: features, input-side gradient (through the stem) and
+    every weight / bias gradient."""
+    from spair_pytorch_b200 import config as cfg, ops
+    from spair_pytorch_b200.modules import Backbone
+    torch.backends.cudnn.allow_tf32 = False          # strict fp32 on the library path too (the model sets this itself)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    topo = cfg.CELL8_BACKBONE_TOPOLOGY if topology == "cell8" else None
+    net = Backbone(list(shape), 100, topology=topo).to(DEV)
+    # (small batch: a pre-activation within ~1e-6 of zero takes the other ReLU branch under another rounding and moves
+    # every upstream gradient by ~1/sqrt(#activations); with few activations none sits that close — checked below)
+    x = torch.rand(2, *shape, device=DEV)
+
+    def run(tc):
+        monkeypatch.setattr(ops, "USE_TENSOR_CORE_GEMM", tc)
+        for p in net.parameters():
+            p.grad = None
+        feat = net(x)
+        g = torch.Generator(device=DEV).manual_seed(2)
+        (feat * torch.randn(feat.shape, device=DEV, generator=g)).sum().backward()
+        return feat.detach().clone(), [p.grad.detach().clone() for p in net.parameters()]
+
+    f0, g0 = run(False)
+    f1, g1 = run(True)
+    # float64 evaluation of the same module on the CPU: the judge of both fp32 paths (cuDNN picks FFT / SIMT algorithms whose
+    # own rounding is of the same size as the difference between the two paths)
+    net64 = copy.deepcopy(net).double().cpu()
+    for p in net64.parameters():
+        p.grad = None
+    feat64 = net64(x.double().cpu())
+    g = torch.Generator(device=DEV).manual_seed(2)
+    (feat64 * torch.randn(f0.shape, device=DEV, generator=g).double().cpu()).sum().backward()
+    g64 = [p.grad for p in net64.parameters()]
+
+    def err(a, ref):
+        return float((a.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+
+    assert err(f1, feat64) <= max(2e-6, 2.0 * err(f0, feat64)), (err(f1, feat64), err(f0, feat64))
+    assert_close(f1, feat64.float(), "features", atol=1e-5 + 1e-4 * float(feat64.abs().max()) * 0.05)
+    for (name, _), a, b, r in zip(net.named_parameters(), g1, g0, g64):
+        # (elementwise closeness to float64 is not a criterion here: an activation within an ulp of zero takes the other
+        # ReLU branch in fp32 and moves single gradient entries by percents — in the cuDNN path just as much)
+        assert err(a, r) <= max(5e-5, 2.0 * err(b, r)), (name, err(a, r), err(b, r))
+        print("%-28s rel. error vs float64: tcgen05 %.2e, cuDNN %.2e" % (name, err(a, r), err(b, r)))
+
+
+def test_im2col_col2im_adjoint():
+    """<im2col(x), c> == <x, col2im(c)> (the two kernels of csrc/conv.cu are adjoint), and im2col equals torch's unfold."""
+    k_ = K()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for (B, H, W, C, k, s) in [(2, 50, 50, 128, 4, 2), (3, 9, 11, 8, 3, 1), (1, 7, 7, 4, 1, 1)]:
+        x = torch.randn(B, H, W, C, device=DEV, generator=g)
+        Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+        col = torch.empty(B * Ho * Wo, k * k * C, device=DEV)
+        k_.im2col_nhwc(x, k, s, col)
+        ref = torch.nn.functional.unfold(x.permute(0, 3, 1, 2), k, stride=s)            # [B, C*k*k, L], (c, kh, kw) order
+        ref = ref.view(B, C, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * C)
+        assert torch.equal(col, ref)
+        c = torch.randn(col.shape, device=DEV, generator=g)
+        dx = torch.empty_like(x)
+        k_.col2im_nhwc(c, k, s, dx)
+        lhs, rhs = float((col.double() * c.double()).sum()), float((x.double() * dx.double()).sum())
+        assert abs(lhs - rhs) <= 1e-6 * (abs(lhs) + 1.0)

@@ -11,7 +11,10 @@ from tests.helpers import assert_close
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 # measured budgets (profiles/r02_parity_escapes.json); see OTHER_SHAPES
-ESCAPE_BUDGET_A32 = 0.0
+# config A, B=32 (BASELINE configs[0]): 5 of the 200,704 elements of object_encoder.dense0.weight.grad (a K = 3,872-row
+# reduction on the 3xTF32 tensor-core GEMM) sit just outside (rtol, atol) of the fp32 reference and inside it of the float64
+# evaluation; no ref_err / kink escapes anywhere.  Budget: 1e-4 of a tensor's elements, float64-clause only in practice.
+ESCAPE_BUDGET_A32 = 1e-4
 ESCAPE_BUDGET_A2500 = 0.5
 # config D, B=1: the weight gradients now come from the 3xTF32 tensor-core GEMM (csrc/gemm.cu), whose rounding differs from
 # the fp32 reference's by ~1e-6 of sum|a||b|.  Measured: 2 of the 2,266,987 checked gradient elements (both in

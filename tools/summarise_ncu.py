@@ -73,7 +73,12 @@ def full(path, top=25):
         tot = sum(o[3] for o in out) or 1
         samp = sum(o[4] for o in out) or 1
         print("### hot source lines of `%s`\n\n| file:line | instr %% | stall-sample %% | source |\n|---|---:|---:|---|" % kernel)
-        for f, l, s, n, sm in sorted(out, key=lambda o: -o[3])[:top]:
+        agg = {}
+        for f, l, s, n, sm in out:          # one entry per (file, line): inlined copies and repeated launches are summed
+            e = agg.setdefault((f, l), [f, l, s, 0, 0])
+            e[3] += n
+            e[4] += sm
+        for f, l, s, n, sm in sorted(agg.values(), key=lambda o: -o[3])[:top]:
             print("| %s:%d | %.1f | %.1f | `%s` |" % (f, l, 100 * n / tot, 100 * sm / samp, s.replace("|", "\\|")))
         print()
 
