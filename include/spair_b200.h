@@ -390,6 +390,16 @@ int spair_im2col_nhwc(const float* x /* [B,H,W,C] */, int B, int H, int W, int C
 int spair_col2im_nhwc(const float* dcol /* [B*Ho*Wo, k*k*C] */, int B, int H, int W, int C, int k, int stride,
                       float* dx /* [B,H,W,C] */, void* stream);
 
+/* out[b][c][r] = in[b][r][c] (NCHW <-> channels-last of a [B, C, H*W] feature map), coalesced both ways. */
+int spair_transpose_batched(const float* in, int B, int R, int C, float* out, void* stream);
+
+/* Bias gradient of a dense / 1x1-conv layer fused with the ReLU mask of its output: if y != NULL, g[r][c] *= (y[r][c] > 0)
+ * in place; out[c] = sum_r g[r][c] (two launches, fixed order).  cols, ld_g, ld_y multiples of 4, 16-byte aligned;
+ * ws: spair_colsum_chunks(rows) * cols floats. */
+int spair_colsum_chunks(int rows);
+int spair_relu_bwd_colsum(float* g, int ld_g, const float* y /* or NULL */, int ld_y, int rows, int cols, float* ws,
+                          float* out /* [cols] */, void* stream);
+
 /* Elementwise helper of the manual MLP backward: dh *= (h > 0), row-strided. */
 int spair_relu_bwd(float* dh, int ld_dh, const float* h, int ld_h, int rows, int cols, void* stream);
 

@@ -56,9 +56,93 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float4* __restri
     }
 }
 
+// out[b][c][r] = in[b][r][c]: 32x32 tiles through shared memory, both sides coalesced (NCHW <-> NHWC of a feature map with
+// R = H*W pixels and C channels per image).
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+    __shared__ float tile[32][33];
+    const size_t base = (size_t)blockIdx.z * R * C;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < R && c0 + tx < C) tile[i][tx] = in[base + (size_t)(r0 + i) * C + c0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < C && r0 + tx < R) out[base + (size_t)(c0 + i) * R + r0 + tx] = tile[tx][i];
+}
+
+// Column sums of a [rows, cols] matrix (the bias gradient of a dense / 1x1 layer), optionally fused with the ReLU mask of
+// the layer's output: g[r][c] *= (y[r][c] > 0) in place, then summed.  Stage 1: CTA (column block of 128, row chunk) keeps
+// per-thread partial sums of 4 adjacent columns (128-bit loads) and adds its 8 warps in shared memory; stage 2 adds the
+// chunks in a fixed order.  Deterministic, one pass over g (and y).
+constexpr int kCsRowsPerCta = 512;
+
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(float* __restrict__ g, int ld_g, const float* __restrict__ y, int ld_y,
+                                                            int rows, int cols, float* __restrict__ partial) {
+    __shared__ float4 red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const int r_begin = blockIdx.y * kCsRowsPerCta, r_end = min(rows, r_begin + kCsRowsPerCta);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cols) {      // cols % 4 == 0 (host)
+#pragma unroll 4
+        for (int r = r_begin + warp; r < r_end; r += 8) {
+            float4 v = *reinterpret_cast<const float4*>(g + (size_t)r * ld_g + c);
+            if (y) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(y + (size_t)r * ld_y + c));
+                v.x = m.x > 0.0f ? v.x : 0.0f; v.y = m.y > 0.0f ? v.y : 0.0f;
+                v.z = m.z > 0.0f ? v.z : 0.0f; v.w = m.w > 0.0f ? v.w : 0.0f;
+                *reinterpret_cast<float4*>(g + (size_t)r * ld_g + c) = v;
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < cols) {
+        float4 s = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
+        *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * cols + c) = s;
+    }
+}
+
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.0f;
+    for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * cols + c];
+    out[c] = s;
+}
+
 }  // namespace spair
 
 using namespace spair;
+
+extern "C" int spair_transpose_batched(const float* in, int B, int R, int C, float* out, void* stream) {
+    SPAIR_REQUIRE(in && out && B > 0 && B <= 65535 && R > 0 && C > 0);
+    dim3 grid((C + 31) / 32, (R + 31) / 32, B);
+    SPAIR_REQUIRE(grid.y <= 65535);
+    transpose_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, R, C);
+    SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_colsum_chunks(int rows) { return (rows + kCsRowsPerCta - 1) / kCsRowsPerCta; }
+
+extern "C" int spair_relu_bwd_colsum(float* g, int ld_g, const float* y, int ld_y, int rows, int cols, float* ws, float* out,
+                                     void* stream) {
+    SPAIR_REQUIRE(g && ws && out && rows > 0 && cols > 0 && (cols & 3) == 0 && (ld_g & 3) == 0 && ((uintptr_t)g & 15) == 0);
+    SPAIR_REQUIRE(!y || ((ld_y & 3) == 0 && ((uintptr_t)y & 15) == 0));
+    const int chunks = spair_colsum_chunks(rows);
+    SPAIR_REQUIRE(chunks <= 65535);
+    dim3 grid((cols + 127) / 128, chunks);
+    colsum_stage1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ld_g, y, ld_y, rows, cols, ws);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    colsum_stage2_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ws, chunks, cols, out);
+    SPAIR_LAUNCH_CHECK();
+}
 
 extern "C" int spair_im2col_nhwc(const float* x, int B, int H, int W, int C, int k, int stride, float* col, void* stream) {
     SPAIR_REQUIRE(x && col && B > 0 && H >= k && W >= k && C > 0 && (C & 3) == 0 && k > 0 && stride > 0);

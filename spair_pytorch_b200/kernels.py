@@ -91,6 +91,9 @@ _SIGNATURES = {
     "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P],
     "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "spair_transpose_batched": [_P, _I, _I, _I, _P, _P],
+    "spair_colsum_chunks": [_I],
+    "spair_relu_bwd_colsum": [_P, _I, _P, _I, _I, _I, _P, _P, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
@@ -416,6 +419,29 @@ def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, per
         LAUNCH_COUNT += 1      # the fixed-order split-K reduction / the ReLU sign fix-up
 
 
+def transpose_batched(x, out):
+    """x [B,R,C] -> out [B,C,R] (both contiguous)."""
+    B, R, C = x.shape
+    _check(lib().spair_transpose_batched(_ptr(_contig(x, "x")), B, R, C, _ptr(_contig(out, "out")), _stream()),
+           "spair_transpose_batched")
+
+
+def relu_bwd_colsum(g, y, out):
+    """In place g *= (y > 0) (skipped when y is None), out[c] = sum_r g[r, c].  Falls back to torch for column counts or
+    row pitches that are not multiples of 4."""
+    rows, cols = g.shape
+    if cols % 4 or g.stride(0) % 4 or g.data_ptr() % 16 or (y is not None and (y.stride(0) % 4 or y.data_ptr() % 16)):
+        if y is not None:
+            relu_bwd(g, y)
+        torch.sum(g, 0, out=out)
+        return
+    ws = _gemm_workspace(g.device, lib().spair_colsum_chunks(rows) * cols)
+    _check(lib().spair_relu_bwd_colsum(_ptr(g), _ld(g), _ptr(y), _ld(y), rows, cols, _ptr(ws), _ptr(_contig(out, "out")), _stream()),
+           "spair_relu_bwd_colsum")
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+
+
 def im2col_nhwc(x, k: int, stride: int, col):
     """x [B,H,W,C] channels-last -> col [B*Ho*Wo, k*k*C] (see spair_im2col_nhwc)."""
     B, H, W, C = x.shape
@@ -588,6 +614,6 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
 # device guard on every launch wrapper (see _device_guarded)
 for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
               "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
-              "sweep_bwd", "gemm3x", "im2col_nhwc", "col2im_nhwc", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+              "sweep_bwd", "gemm3x", "im2col_nhwc", "col2im_nhwc", "transpose_batched", "relu_bwd_colsum", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
     globals()[_name] = _device_guarded(globals()[_name])
 del _name

@@ -291,9 +291,10 @@ class _ManualMLP:
                 # dW[n_out, n_in] = g^T i, both operands MN-major as stored (a head output of 102 or 1 columns is first
                 # copied to a 16-byte row pitch: 12 MB, against a 30976-row reduction)
                 K.gemm3x(_tma_rows(g), False, _tma_rows(i), False, dW)
+                K.relu_bwd_colsum(g, None, db)
             else:
                 torch.mm(g.t(), i, out=dW)
-            torch.sum(g, 0, out=db)
+                torch.sum(g, 0, out=db)
         return self.dW, self.db
 
 
@@ -333,19 +334,20 @@ class DecoderFunction(torch.autograd.Function):
         n, dev = attr.shape[0], attr.device
         d_w2 = torch.empty_like(w2)
         K.gemm3x(d_logits, False, h1, False, d_w2)
-        d_b2 = d_logits.sum(0)
+        d_b2 = torch.empty(w2.shape[0], device=dev, dtype=torch.float32)
+        K.relu_bwd_colsum(d_logits, None, d_b2)
         d_h1 = torch.empty_like(h1)
         K.gemm3x(d_logits, True, w2, False, d_h1)
-        K.relu_bwd(d_h1, h1)
+        d_b1 = torch.empty(w1.shape[0], device=dev, dtype=torch.float32)
+        K.relu_bwd_colsum(d_h1, h1, d_b1)
         d_w1 = torch.empty_like(w1)
         K.gemm3x(d_h1, False, h0, False, d_w1)
-        d_b1 = d_h1.sum(0)
         d_h0 = torch.empty_like(h0)
         K.gemm3x(d_h1, True, w1, False, d_h0)
-        K.relu_bwd(d_h0, h0)
+        d_b0 = torch.empty(w0.shape[0], device=dev, dtype=torch.float32)
+        K.relu_bwd_colsum(d_h0, h0, d_b0)
         d_w0 = torch.empty_like(w0)
         K.gemm3x(d_h0, False, attr, False, d_w0)
-        d_b0 = d_h0.sum(0)
         d_attr = None
         if ctx.needs_input_grad[0]:
             d_attr = torch.empty_like(attr)
@@ -415,7 +417,9 @@ class ConvTailFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y0, specs, *params):
-        x = y0.permute(0, 2, 3, 1).contiguous()                     # channels-last from here on
+        B0, C0, H0, W0 = y0.shape
+        x = torch.empty(B0, H0, W0, C0, device=y0.device, dtype=torch.float32)      # channels-last from here on
+        K.transpose_batched(y0.contiguous().view(B0, C0, H0 * W0), x.view(B0, H0 * W0, C0))
         saved, shapes = [], []
         for li, (k, s, relu) in enumerate(specs):
             w, b = params[2 * li].detach(), params[2 * li + 1].detach().contiguous()
@@ -435,24 +439,28 @@ class ConvTailFunction(torch.autograd.Function):
             x = y.view(Bn, Ho, Wo, w.shape[0])
         ctx.save_for_backward(*saved)
         ctx.specs, ctx.shapes = specs, shapes
-        return x.permute(0, 3, 1, 2).contiguous()
+        Bn, Ho, Wo, F = x.shape
+        feat = torch.empty(Bn, F, Ho, Wo, device=x.device, dtype=torch.float32)
+        K.transpose_batched(x.view(Bn, Ho * Wo, F), feat.view(Bn, F, Ho * Wo))
+        return feat
 
     @staticmethod
     def backward(ctx, d_feat):
         specs, shapes, saved = ctx.specs, ctx.shapes, ctx.saved_tensors
         Bn, _, _, _, Ho, Wo, wshape = shapes[-1]
-        dy = d_feat.permute(0, 2, 3, 1).reshape(Bn * Ho * Wo, wshape[0]).contiguous()
+        dy = torch.empty(Bn * Ho * Wo, wshape[0], device=d_feat.device, dtype=torch.float32)
+        K.transpose_batched(d_feat.contiguous().view(Bn, wshape[0], Ho * Wo), dy.view(Bn, Ho * Wo, wshape[0]))
         grads = [None] * (2 * len(specs))
         for li in range(len(specs) - 1, -1, -1):
             k, s, relu = specs[li]
             a, wr, y = saved[3 * li: 3 * li + 3]
             Bn, H, W, Cin, Ho, Wo, wshape = shapes[li]
-            if relu:
-                K.relu_bwd(dy, y)
+            db = torch.empty(wshape[0], device=dy.device, dtype=torch.float32)
+            K.relu_bwd_colsum(dy, y if relu else None, db)            # ReLU mask (in place) + bias gradient, one pass
             d_wr = torch.empty_like(wr)
             K.gemm3x(dy, False, a, False, d_wr)
             grads[2 * li] = d_wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2).contiguous()
-            grads[2 * li + 1] = dy.sum(0)
+            grads[2 * li + 1] = db
             if li == 0 and not ctx.needs_input_grad[0]:
                 return (None, None) + tuple(grads)
             da = torch.empty_like(a)
@@ -464,7 +472,9 @@ class ConvTailFunction(torch.autograd.Function):
                 K.col2im_nhwc(da, k, s, dx)
                 dy = dx.view(Bn * H * W, Cin)
         Bn, H, W, Cin = shapes[0][:4]
-        return (dy.view(Bn, H, W, Cin).permute(0, 3, 1, 2).contiguous(), None) + tuple(grads)
+        d_y0 = torch.empty(Bn, Cin, H, W, device=dy.device, dtype=torch.float32)
+        K.transpose_batched(dy.view(Bn, H * W, Cin), d_y0.view(Bn, Cin, H * W))
+        return (d_y0, None) + tuple(grads)
 
 
 class CellSweepFunction(torch.autograd.Function):

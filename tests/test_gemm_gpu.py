@@ -203,3 +203,27 @@ def test_im2col_col2im_adjoint():
         k_.col2im_nhwc(c, k, s, dx)
         lhs, rhs = float((col.double() * c.double()).sum()), float((x.double() * dx.double()).sum())
         assert abs(lhs - rhs) <= 1e-6 * (abs(lhs) + 1.0)
+
+
+def test_transpose_and_relu_bwd_colsum():
+    """Layout / reduction helpers of csrc/conv.cu: batched transpose (NCHW <-> channels-last) is an exact permutation;
+    the fused ReLU-mask + bias-gradient pass equals torch's mask and column sum (bitwise mask, sum to fp32 rounding)
+    and is run-to-run reproducible."""
+    k_ = K()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    for (B, R, C) in [(3, 2500, 128), (2, 121, 100), (1, 33, 7)]:
+        x = torch.randn(B, R, C, device=DEV, generator=g)
+        out = torch.empty(B, C, R, device=DEV)
+        k_.transpose_batched(x, out)
+        assert torch.equal(out, x.transpose(1, 2).contiguous())
+    for (rows, cols, masked) in [(30976, 1568, False), (3000, 128, True), (7, 4, True), (1000, 102, False), (513, 100, True)]:
+        gr = torch.randn(rows, cols, device=DEV, generator=g)
+        y = torch.randn(rows, cols, device=DEV, generator=g).clamp_min(0) if masked else None
+        want_g = gr * (y > 0) if masked else gr.clone()
+        want = want_g.double().sum(0)
+        a, b = gr.clone(), gr.clone()
+        o1, o2 = torch.empty(cols, device=DEV), torch.empty(cols, device=DEV)
+        k_.relu_bwd_colsum(a, y, o1)
+        k_.relu_bwd_colsum(b, y, o2)
+        assert torch.equal(a, want_g) and torch.equal(o1, o2)
+        assert_close(o1, want.float(), "column sums", atol=1e-5 + 1e-6 * float(want_g.abs().sum(0).max()))
