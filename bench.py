@@ -446,26 +446,39 @@ class Workload:
         if self.eager:
             self.x_stage.copy_(hb[i % len(hb)], non_blocking=True)  # H2D from pinned memory
             loss = self.fwd_bwd(self.x_stage, STEP0 + i)[0]
-        else:
-            # input double buffering (GraphedTrainStep.prefetch): this step consumes the batch whose H2D copy was started
-            # during the previous step and starts the copy of the next one, which overlaps this step's kernels.  Every
-            # timed step still performs exactly one pinned H2D copy of a whole batch and one D2H read inside the timed region.
-            if not self.gstep._has_staged:
-                self.gstep.prefetch(hb[i % len(hb)])
-            loss = self.fwd_bwd(None, STEP0 + i)[0]
-            self.gstep.prefetch(hb[(i + 1) % len(hb)])
+            self.opt.step()
+            self.loss_host.copy_(loss.detach(), non_blocking=False)                      # D2H read of the loss
+            return
+        # input double buffering (GraphedTrainStep.prefetch): this step consumes the batch whose H2D copy was started
+        # during the previous step and starts the copy of the next one, which overlaps this step's kernels.  The loss is
+        # read through GraphedTrainStep.loss_async(): its D2H copy is queued right behind the step and the host waits for
+        # it one step later, after it has launched the next step.  Every timed step still performs exactly one pinned H2D
+        # copy of a whole batch and one D2H read of a loss inside the timed region (the last one in drain_e2e()).
+        if not self.gstep._has_staged:
+            self.gstep.prefetch(hb[i % len(hb)])
+        self.fwd_bwd(None, STEP0 + i)
+        self.gstep.prefetch(hb[(i + 1) % len(hb)])
         self.opt.step()
-        self.loss_host.copy_(loss.detach(), non_blocking=False)                          # D2H read of the loss
+        pending, self._pending_loss = getattr(self, "_pending_loss", None), self.gstep.loss_async()
+        if pending is not None:
+            self.last_loss = pending.value()
+
+    def drain_e2e(self):
+        pending, self._pending_loss = getattr(self, "_pending_loss", None), None
+        if pending is not None:
+            self.last_loss = pending.value()
 
     def barrier(self):
         if self.world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(self, fn, steps, warmup, local_rank=0):
+    def timed(self, fn, steps, warmup, local_rank=0, finish=None):
         K = self.K
         for i in range(warmup):
             fn(i)
+        if finish is not None:
+            finish()
         self.barrier()
         n0 = K.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -473,6 +486,8 @@ class Workload:
             e0.record()
             for i in range(steps):
                 fn(warmup + i)
+            if finish is not None:
+                finish()                     # e.g. the D2H read of the last step's loss: inside the timed region
             e1.record()
             self.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
@@ -493,7 +508,7 @@ def secondary_workload(config_name, global_batch, scaling, rank, world, dev, loc
     per_gpu = global_batch // world if scaling == "strong" else global_batch
     wl = Workload(config_name, per_gpu, rank, world, dev)
     ms, launches, clocks = wl.timed(wl.step_resident, steps, warmup, local_rank)
-    ms_e2e, _, _ = wl.timed(wl.step_e2e, steps, max(warmup, 3), local_rank)
+    ms_e2e, _, _ = wl.timed(wl.step_e2e, steps, max(warmup, 3), local_rank, finish=wl.drain_e2e)
     block = {"workload": "BASELINE %s, batch %d per GPU (%s scaling, global batch %d), step = zero_grad+fwd+bwd+Adam%s"
                          % (workload_name(config_name), per_gpu, scaling, per_gpu * world, "+NCCL grad allreduce" if world > 1 else ""),
              "scaling": scaling, "n_gpus": world, "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "steps": steps,
@@ -532,7 +547,7 @@ def run_ours(args):
         torch.cuda.profiler.stop()
         return None
     ms_res, launches, clocks = wl.timed(wl.step_resident, args.steps, args.warmup, local_rank)
-    ms_e2e, _, _ = wl.timed(wl.step_e2e, args.steps, max(args.warmup, 3), local_rank)
+    ms_e2e, _, _ = wl.timed(wl.step_e2e, args.steps, max(args.warmup, 3), local_rank, finish=wl.drain_e2e)
     value = world * B / (ms_res * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
 
@@ -556,8 +571,10 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": world * wl.host_batches[0].numel() * 4,
                     "d2h_bytes_per_step": world * 4,
                     "note": "public API GraphedTrainStep with host batches in pinned memory: one H2D copy of a whole batch "
-                            "and one blocking D2H read of the loss per step, both inside the timed region; the H2D copy of "
-                            "step i+1 is issued on a copy stream while step i runs (input double buffering)"
+                            "and one D2H read of that step's loss per step, all inside the timed region; the H2D copy of step i+1 is "
+                            "issued on a copy stream while step i runs (input double buffering) and the host waits for the "
+                            "loss of step i after it has launched step i+1 (GraphedTrainStep.loss_async; the last loss is "
+                            "read before the closing event)"
                             if not args.eager else "eager step: H2D copy, forward, backward, Adam, blocking D2H loss read"},
             "gpu_launches": launches,
             "roofline": roof,

@@ -291,14 +291,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint32_t addr = s0 + c * 16;
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-                    uint32_t h0 = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u, h1 = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
-                    uint32_t h2 = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u, h3 = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
+                    // debug 8: hi = the raw word (valid only if the tensor core TRUNCATES the low 13 mantissa bits of a tf32
+                    // operand), so only lo is written
+                    const uint32_t rnd = (p.debug & 8) ? 0u : 0x1000u;
+                    uint32_t h0 = (__float_as_uint(v.x) + rnd) & 0xffffe000u, h1 = (__float_as_uint(v.y) + rnd) & 0xffffe000u;
+                    uint32_t h2 = (__float_as_uint(v.z) + rnd) & 0xffffe000u, h3 = (__float_as_uint(v.w) + rnd) & 0xffffe000u;
                     // lo = x - hi is exact in fp32 (13 significant bits); rounded to TF32 here (the tensor core would truncate it)
                     const uint32_t l0 = (__float_as_uint(v.x - __uint_as_float(h0)) + 0x1000u) & 0xffffe000u;
                     const uint32_t l1 = (__float_as_uint(v.y - __uint_as_float(h1)) + 0x1000u) & 0xffffe000u;
                     const uint32_t l2 = (__float_as_uint(v.z - __uint_as_float(h2)) + 0x1000u) & 0xffffe000u;
                     const uint32_t l3 = (__float_as_uint(v.w - __uint_as_float(h3)) + 0x1000u) & 0xffffe000u;
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                    if (!(p.debug & 8)) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + kLoOff), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async reads

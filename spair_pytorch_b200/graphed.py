@@ -20,6 +20,15 @@ import torch
 from .dp import GradientBucket, trainable_parameters
 
 
+class _PendingLoss:
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def value(self) -> float:
+        self._event.synchronize()
+        return float(self._host)
+
+
 class GraphedTrainStep:
     def __init__(self, net, example_x: torch.Tensor, bucket: GradientBucket = None, global_step: int = 1000, warmup: int = 3):
         if not example_x.is_cuda:
@@ -73,6 +82,22 @@ class GraphedTrainStep:
             self._staged.copy_(x_host, non_blocking=True)
             self._staged_ready.record(self._copy_stream)
         self._has_staged = True
+
+    def loss_async(self):
+        """Non-blocking read of the step that was just launched: snapshots the (static) loss output, starts its D2H copy
+        into pinned memory and returns a handle whose ``value()`` waits for that copy only.  Calling ``value()`` one step
+        later (after the next step has been launched) keeps the host one step ahead of the GPU, so the per-step launch work
+        of the host (schedule refresh, graph launch, optimiser launch) overlaps the previous step's kernels."""
+        dev = self.static_x.device
+        if not hasattr(self, "_loss_ring"):
+            self._loss_ring = [(torch.empty((), device=dev), torch.empty((), pin_memory=True), torch.cuda.Event()) for _ in range(4)]
+            self._loss_slot = 0
+        snap, host, ev = self._loss_ring[self._loss_slot]
+        self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+        snap.copy_(self.out[0].detach(), non_blocking=True)
+        host.copy_(snap, non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
+        return _PendingLoss(host, ev)
 
     def __call__(self, x, global_step: int):
         """Runs one captured step on ``x`` (device tensor, or pinned host tensor — copied asynchronously; ``None`` = the

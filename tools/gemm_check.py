@@ -69,6 +69,9 @@ if __name__ == "__main__":
     if "--decoder-only" in sys.argv:
         check("decoder out fwd (plain)", 30976, 1568, 256, 1, 1)
         check("decoder out fwd (texel)", 30976, 1568, 256, 1, 1, epilogue=2)
+        check("conv_1 fwd", 147456, 128, 2048, 1, 1, epilogue=1)
+        check("conv_1 dgrad", 147456, 2048, 128, 1, 0, bias=False)
+        check("conv_1 wgrad", 128, 2048, 147456, 0, 0, bias=False)
         sys.exit(0)
     # small shapes first: one tile, one k-block, each major combination
     for a_k in (1, 0):
