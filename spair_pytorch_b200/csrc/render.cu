@@ -49,6 +49,7 @@ struct RenderArgs {
     float* bce_partial;
     int group;        // objects staged per round
     int slot_f4;      // float4 records per slot (= G*G*NF4)
+    int table_off;    // byte offset of the per-object coordinate tables in dynamic shared memory
 };
 
 template <int C>
@@ -113,6 +114,11 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     float4* slots = reinterpret_cast<float4*>(smem_raw);
     float4* aff = slots + (size_t)p.group * p.slot_f4;                          // [HW] inverse affine of kept objects
     unsigned short* list = reinterpret_cast<unsigned short*>(aff + p.HW);       // [HW] kept object ids, cell order
+    // per staged object: 32 column entries {xa, xb (float4 offsets of the two taps), wx0, wx1} and 32 row entries
+    // {ya, yb, wy0, wy1} of this tile; xa / ya < 0 marks a column / row whose sample falls outside the texture
+    float4* colT = reinterpret_cast<float4*>(smem_raw + p.table_off);            // [group][32]
+    float4* rowT = colT + (size_t)p.group * kRTileW;                             // [group][32]
+    __shared__ float bXs[kRTileW], bYs[kRTileH];
     __shared__ int warp_cnt[kRThreads / 32];
     __shared__ int list_len;
     __shared__ float red[kRThreads / 32];
@@ -162,18 +168,15 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
     const int tx = threadIdx.x & (kRTileW - 1), ty = threadIdx.x / kRTileW;
     const int X = X0 + tx;
     const bool px_ok = X < p.Iw;
-    const float bX = base_coord(min(X, p.Iw - 1), p.Iw);
-    float bY[kRPPT];
     bool ok[kRPPT];
 #pragma unroll
-    for (int h = 0; h < kRPPT; ++h) {
-        const int Y = Y0 + ty + (kRThreads / kRTileW) * h;
-        ok[h] = px_ok && Y < p.Ih;
-        bY[h] = base_coord(min(Y, p.Ih - 1), p.Ih);
-    }
+    for (int h = 0; h < kRPPT; ++h) ok[h] = px_ok && (Y0 + ty + (kRThreads / kRTileW) * h) < p.Ih;
+    if (threadIdx.x < kRTileW) bXs[threadIdx.x] = base_coord(min(X0 + (int)threadIdx.x, p.Iw - 1), p.Iw);
+    else if (threadIdx.x < kRTileW + kRTileH) bYs[threadIdx.x - kRTileW] = base_coord(min(Y0 + (int)threadIdx.x - kRTileW, p.Ih - 1), p.Ih);
     const float bX0 = base_coord(X0, p.Iw), bX1 = base_coord(X1, p.Iw);
     const float bY0 = base_coord(Y0, p.Ih), bY1 = base_coord(Y1, p.Ih);
     const float hG = 0.5f * (float)G;
+    __syncthreads();
 
     float num[kRPPT][C];
     float den[kRPPT];
@@ -220,31 +223,44 @@ __global__ void __launch_bounds__(kRThreads) render_fwd_kernel(RenderArgs p) {
                     slot[(size_t)tex * NF4 + q] = make_float4(o.v[4 * q], o.v[4 * q + 1], o.v[4 * q + 2], o.v[4 * q + 3]);
             }
         }
+        // coordinate tables of the group: one entry per (object, tile column) and (object, tile row), computed ONCE per CTA
+        // (every thread of a column / row would otherwise redo the same affine + floor + clamp arithmetic per object)
+        for (int idx = threadIdx.x; idx < gcount * (kRTileW + kRTileH); idx += kRThreads) {
+            const int s = idx / (kRTileW + kRTileH), e = idx - s * (kRTileW + kRTileH);
+            const float4 A = aff[g0 + s];
+            const bool is_col = e < kRTileW;
+            const int i = is_col ? e : e - kRTileW;
+            const bool inside = is_col ? (X0 + i < p.Iw) : (Y0 + i < p.Ih);
+            const float ic = unnormalize(is_col ? affine_coord(bXs[i], A.x, A.y) : affine_coord(bYs[i], A.z, A.w), hG);
+            const float f0 = floorf(ic);
+            const bool valid = inside && f0 >= -1.0f && f0 <= (float)(G - 1);
+            const int c0 = (int)f0;
+            const float w1 = (c0 + 1 <= G - 1) ? ic - f0 : 0.0f, w0 = (c0 >= 0) ? f0 + 1.0f - ic : 0.0f;
+            const int ca = max(c0, 0), cb = min(c0 + 1, G - 1);
+            const int unit = is_col ? NF4 : G * NF4;
+            const float4 ent = make_float4(__int_as_float(valid ? ca * unit : -1), __int_as_float(cb * unit), w0, w1);
+            if (is_col) colT[s * kRTileW + i] = ent;
+            else rowT[s * kRTileH + i] = ent;
+        }
         __syncthreads();
         for (int s = 0; s < gcount; ++s) {
-            const float4 A = aff[g0 + s];
             const float4* slot = slots + (size_t)s * p.slot_f4;
-            const float ix = unnormalize(affine_coord(bX, A.x, A.y), hG);
-            const float fx0 = floorf(ix);
-            if (!(fx0 >= -1.0f && fx0 <= (float)(G - 1))) continue;
-            const int x0 = (int)fx0;
-            const float wx1 = (x0 + 1 <= G - 1) ? ix - fx0 : 0.0f, wx0 = (x0 >= 0) ? fx0 + 1.0f - ix : 0.0f;
-            const int xa = max(x0, 0), xb = min(x0 + 1, G - 1);
+            const float4 cT = colT[s * kRTileW + tx];
+            const int xa = __float_as_int(cT.x), xb = __float_as_int(cT.y);
+            if (xa < 0) continue;
+            const float wx0 = cT.z, wx1 = cT.w;
 #pragma unroll
             for (int h = 0; h < kRPPT; ++h) {
-                if (!ok[h]) continue;
-                const float iy = unnormalize(affine_coord(bY[h], A.z, A.w), hG);
-                const float fy0 = floorf(iy);
-                if (!(fy0 >= -1.0f && fy0 <= (float)(G - 1))) continue;
-                const int y0 = (int)fy0;
-                const float wy1 = (y0 + 1 <= G - 1) ? iy - fy0 : 0.0f, wy0 = (y0 >= 0) ? fy0 + 1.0f - iy : 0.0f;
-                const int ya = max(y0, 0), yb = min(y0 + 1, G - 1);
+                const float4 rT = rowT[s * kRTileH + ty + (kRThreads / kRTileW) * h];
+                const int ya = __float_as_int(rT.x), yb = __float_as_int(rT.y);
+                if (ya < 0) continue;
+                const float wy0 = rT.z, wy1 = rT.w;
                 const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0), sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
                 float acc[NF4 * 4];
 #pragma unroll
                 for (int q = 0; q < NF4; ++q) {
-                    const float4 t00 = slot[(size_t)(ya * G + xa) * NF4 + q], t01 = slot[(size_t)(ya * G + xb) * NF4 + q];
-                    const float4 t10 = slot[(size_t)(yb * G + xa) * NF4 + q], t11 = slot[(size_t)(yb * G + xb) * NF4 + q];
+                    const float4 t00 = slot[ya + xa + q], t01 = slot[ya + xb + q];
+                    const float4 t10 = slot[yb + xa + q], t11 = slot[yb + xb + q];
                     acc[4 * q + 0] = fmaf(t11.x, se, fmaf(t10.x, sw, fmaf(t01.x, ne, __fmul_rn(t00.x, nw))));
                     acc[4 * q + 1] = fmaf(t11.y, se, fmaf(t10.y, sw, fmaf(t01.y, ne, __fmul_rn(t00.y, nw))));
                     acc[4 * q + 2] = fmaf(t11.z, se, fmaf(t10.z, sw, fmaf(t01.z, ne, __fmul_rn(t00.z, nw))));
@@ -612,8 +628,10 @@ static int launch_fwd(const RenderArgs& a, cudaStream_t st) {
     if (group < 1) group = 1;
     p.group = group;
     p.slot_f4 = slot_f4;
-    const size_t smem = group * slot_bytes + (size_t)p.HW * sizeof(float4) +
-                        (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
+    const size_t table_off = group * slot_bytes + (size_t)p.HW * sizeof(float4) +
+                             (((size_t)p.HW * sizeof(unsigned short) + 15) & ~(size_t)15);
+    p.table_off = (int)table_off;
+    const size_t smem = table_off + (size_t)group * (kRTileW + kRTileH) * sizeof(float4);
     if (smem > 200 * 1024) return SPAIR_ERR_INVALID;
     static size_t smem_set[kMaxDevices] = {0};
     if (ensure_dynamic_smem(render_fwd_kernel<C>, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
@@ -657,7 +675,7 @@ extern "C" int spair_render_fwd(const float* logits, const float* z_where, const
     SPAIR_REQUIRE((target == nullptr) == (bce_partial == nullptr));
     SPAIR_REQUIRE(((uintptr_t)z_where % 16) == 0 && ((uintptr_t)logits % 16) == 0);
     RenderArgs a{logits, z_where, z_depth, z_pres, B, HW, G, Ih, Iw, obj_scale, alpha_scale, alpha_bias, decoded,
-                 recon, denom, target, bce_partial, 0, 0};
+                 recon, denom, target, bce_partial, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
         case 1: return launch_fwd<1>(a, st);

@@ -117,6 +117,26 @@ class SPAIR(nn.Module):
         self._noise = (img_major(eps_where), img_major(eps_attr), img_major(eps_depth).squeeze(-1).contiguous(),
                        img_major(u_pres).squeeze(-1).contiguous())
 
+    def set_reference_noise(self, batch_size, generator=None, keep=False):
+        """Draws the noise of the next forward exactly as the reference would consume the CPU RNG stream, so that
+        ``torch.manual_seed(s); net.set_reference_noise(B); net(x, step)`` reproduces
+        ``torch.manual_seed(s); reference_net(x, step)`` on the CPU ("same inputs and seeds").  Order of the reference's
+        draws (models.py:333-336,83-85,92-97,402-403 inside the row-major cell loop models.py:68-117): per cell
+        ``normal[B,1]`` x4 (cy, cx, height, width), ``normal[B,A]``, ``normal[B,1]``, ``uniform[B,1]``.
+        ``generator``: a CPU ``torch.Generator`` (default: the global CPU generator, like the reference)."""
+        _, Hc, Wc = (int(v) for v in self.feature_space_dim)
+        A = self._cfg.n_attr
+        eps_where, eps_attr = torch.empty(batch_size, 4, Hc, Wc), torch.empty(batch_size, A, Hc, Wc)
+        eps_depth, u_pres = torch.empty(batch_size, 1, Hc, Wc), torch.empty(batch_size, 1, Hc, Wc)
+        for h in range(Hc):
+            for w in range(Wc):
+                for k in range(4):
+                    eps_where[:, k, h, w] = torch.empty(batch_size, 1).normal_(generator=generator)[:, 0]
+                eps_attr[:, :, h, w] = torch.empty(batch_size, A).normal_(generator=generator)
+                eps_depth[:, :, h, w] = torch.empty(batch_size, 1).normal_(generator=generator)
+                u_pres[:, :, h, w] = torch.rand(batch_size, 1, generator=generator)
+        self.set_noise(eps_where, eps_attr, eps_depth, u_pres, keep=keep)
+
     def _draw_noise(self, B, HW, device):
         A = self._cfg.n_attr
         if self._noise is not None:

@@ -56,6 +56,26 @@ def test_draw_noise_replays_reference_stream():
     assert np.array_equal(n.eps_where.numpy(), g["eps_where"]) and np.array_equal(n.u_pres.numpy(), g["u_pres"])
 
 
+def test_product_reference_noise_stream_matches_reference_golden():
+    """SPAIR.set_reference_noise (product side, no oracle import): seeding the CPU generator like the reference run that
+    produced the golden and replaying its draw order gives the golden's noise tensors bit for bit, i.e. the drop-in can be
+    fed "the same inputs and seeds" as the reference without test infrastructure."""
+    for name in ("tiny", "A"):
+        g = helpers.load_golden("model_%s_step1.npz" % name)
+        net = helpers.build_model(name, "cpu")
+        torch.manual_seed(int(g["noise_seed"]))
+        net.set_reference_noise(g["x"].shape[0])
+        eps_where, eps_attr, eps_depth, u_pres = net._noise           # image-major [B, HW, k] copies held for the next forward
+        B = g["x"].shape[0]
+
+        def img_major(a):
+            t = torch.from_numpy(a)
+            return t.permute(0, 2, 3, 1).reshape(B, -1, t.shape[1])
+
+        assert torch.equal(eps_where, img_major(g["eps_where"])) and torch.equal(eps_attr, img_major(g["eps_attr"]))
+        assert torch.equal(eps_depth, img_major(g["eps_depth"]).squeeze(-1)) and torch.equal(u_pres, img_major(g["u_pres"]).squeeze(-1))
+
+
 def test_closed_form_kl_scan_matches_oracle():
     """fp64 restatement of the count-prior recurrence against the oracle's op sequence."""
     torch.manual_seed(0)
