@@ -320,10 +320,12 @@ def kernel_roofline(net, x, steps=20):
 
 # per-launch DRAM traffic (bytes read + written) from `ncu --set full` captures at config B; (bytes, source)
 NCU_TRAFFIC = {
-    "render_bwd": (228623872 + 159112192, "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)"),
-    "render_fwd": (201631488 + 24653056, "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)"),
-    "glimpse_fwd": (17969920 + 44048128, "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)"),
-    "glimpse_bwd": (115137792 + 4571392, "profiles/r01_warp_kernels_final_full.md (ncu --set full, per launch)"),
+    "sweep_fwd": (48570368 + 383217000, "profiles/r02_kernels_full.md (ncu --set full, per launch)"),
+    "sweep_bwd": (196361728 + 365944000, "profiles/r02_kernels_full.md (ncu --set full, per launch)"),
+    "render_bwd": (228634368 + 159153000, "profiles/r02_kernels_full.md (ncu --set full, per launch, texel-record input)"),
+    "render_fwd": (197374976 + 23060000, "profiles/r02_kernels_full.md (ncu --set full, per launch, texel-record input)"),
+    "glimpse_fwd": (18863616 + 40622080, "profiles/r02_glimpse_full.md (ncu --set full, per launch)"),
+    "glimpse_bwd": (119411456 + 4429056, "profiles/r02_glimpse_full.md (ncu --set full, per launch)"),
 }
 
 

@@ -395,8 +395,8 @@ int spair_transpose_batched(const float* in, int B, int R, int C, float* out, vo
 
 /* Bias gradient of a dense / 1x1-conv layer fused with the ReLU mask of its output: if y != NULL, g[r][c] *= (y[r][c] > 0)
  * in place; out[c] = sum_r g[r][c] (two launches, fixed order).  cols, ld_g, ld_y multiples of 4, 16-byte aligned;
- * ws: spair_colsum_chunks(rows) * cols floats. */
-int spair_colsum_chunks(int rows);
+ * ws: spair_colsum_chunks(rows, cols) * cols floats. */
+int spair_colsum_chunks(int rows, int cols);
 int spair_relu_bwd_colsum(float* g, int ld_g, const float* y /* or NULL */, int ld_y, int rows, int cols, float* ws,
                           float* out /* [cols] */, void* stream);
 

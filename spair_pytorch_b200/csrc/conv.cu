@@ -76,10 +76,18 @@ __global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __r
 // the layer's output: g[r][c] *= (y[r][c] > 0) in place, then summed.  Stage 1: CTA (column block of 128, row chunk) keeps
 // per-thread partial sums of 4 adjacent columns (128-bit loads) and adds its 8 warps in shared memory; stage 2 adds the
 // chunks in a fixed order.  Deterministic, one pass over g (and y).
-constexpr int kCsRowsPerCta = 512;
+// rows per CTA: enough chunks to put >= 4 CTAs on every SM whatever the column count (a [30976, 128] gradient has ONE
+// column block), at least 32 rows each
+static int colsum_rows_per_cta(int rows, int cols) {
+    const int col_blocks = (cols + 127) / 128;
+    int chunks = (4 * kSMs + col_blocks - 1) / col_blocks;
+    if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+    if (chunks < 1) chunks = 1;
+    return (rows + chunks - 1) / chunks;
+}
 
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(float* __restrict__ g, int ld_g, const float* __restrict__ y, int ld_y,
-                                                            int rows, int cols, float* __restrict__ partial) {
+                                                            int rows, int cols, int kCsRowsPerCta, float* __restrict__ partial) {
     __shared__ float4 red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 128 + lane * 4;
@@ -128,16 +136,20 @@ extern "C" int spair_transpose_batched(const float* in, int B, int R, int C, flo
     SPAIR_LAUNCH_CHECK();
 }
 
-extern "C" int spair_colsum_chunks(int rows) { return (rows + kCsRowsPerCta - 1) / kCsRowsPerCta; }
+extern "C" int spair_colsum_chunks(int rows, int cols) {
+    const int per = colsum_rows_per_cta(rows, cols);
+    return (rows + per - 1) / per;
+}
 
 extern "C" int spair_relu_bwd_colsum(float* g, int ld_g, const float* y, int ld_y, int rows, int cols, float* ws, float* out,
                                      void* stream) {
     SPAIR_REQUIRE(g && ws && out && rows > 0 && cols > 0 && (cols & 3) == 0 && (ld_g & 3) == 0 && ((uintptr_t)g & 15) == 0);
     SPAIR_REQUIRE(!y || ((ld_y & 3) == 0 && ((uintptr_t)y & 15) == 0));
-    const int chunks = spair_colsum_chunks(rows);
+    const int per = colsum_rows_per_cta(rows, cols);
+    const int chunks = (rows + per - 1) / per;
     SPAIR_REQUIRE(chunks <= 65535);
     dim3 grid((cols + 127) / 128, chunks);
-    colsum_stage1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ld_g, y, ld_y, rows, cols, ws);
+    colsum_stage1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ld_g, y, ld_y, rows, cols, per, ws);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     colsum_stage2_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ws, chunks, cols, out);

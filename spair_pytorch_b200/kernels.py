@@ -92,7 +92,7 @@ _SIGNATURES = {
     "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_transpose_batched": [_P, _I, _I, _I, _P, _P],
-    "spair_colsum_chunks": [_I],
+    "spair_colsum_chunks": [_I, _I],
     "spair_relu_bwd_colsum": [_P, _I, _P, _I, _I, _I, _P, _P, _P],
     "spair_sweep_max_rows": [],
     "spair_sweep_pack_weights": [_P, _I, _P],
@@ -435,7 +435,7 @@ def relu_bwd_colsum(g, y, out):
             relu_bwd(g, y)
         torch.sum(g, 0, out=out)
         return
-    ws = _gemm_workspace(g.device, lib().spair_colsum_chunks(rows) * cols)
+    ws = _gemm_workspace(g.device, lib().spair_colsum_chunks(rows, cols) * cols)
     _check(lib().spair_relu_bwd_colsum(_ptr(g), _ld(g), _ptr(y), _ld(y), rows, cols, _ptr(ws), _ptr(_contig(out, "out")), _stream()),
            "spair_relu_bwd_colsum")
     global LAUNCH_COUNT
