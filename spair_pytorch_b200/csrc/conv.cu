@@ -116,12 +116,14 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(float* __restrict__ 
     }
 }
 
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: lane l adds chunks l, l + 32, ... in order, then a fixed butterfly (deterministic)
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= cols) return;
     float s = 0.0f;
-    for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * cols + c];
-    out[c] = s;
+    for (int k = lane; k < chunks; k += 32) s += partial[(size_t)k * cols + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
 }
 
 }  // namespace spair
@@ -152,7 +154,7 @@ extern "C" int spair_relu_bwd_colsum(float* g, int ld_g, const float* y, int ld_
     colsum_stage1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ld_g, y, ld_y, rows, cols, per, ws);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    colsum_stage2_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ws, chunks, cols, out);
+    colsum_stage2_kernel<<<(cols + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ws, chunks, cols, out);
     SPAIR_LAUNCH_CHECK();
 }
 

@@ -252,7 +252,13 @@ class SPAIR(nn.Module):
         z_where, attr, depth, pres, dmean, dstd, box = ops.CellSweepFunction.apply(
             plan, x, feat, self.virtual_edge_element, *noise, wheel, *self._sweep_params())
 
-        # decoder MLP over all N = B*HW objects at once (reference models.py:474-481), cuBLAS
+        # KL terms + count-prior scan (models.py:169-262): launched on a side stream, joined after the renderer
+        kl_sync = {}
+        kl_side = plan.side_streams(dev, 1)[0] if dev.type == "cuda" and "SPAIR_SERIAL_KL" not in os.environ else None
+        kl_sums, kl_map = ops.KLFunction.apply(dmean, dstd, pres, plan.prior_mean, plan.prior_std, count_dist0, c.n_attr,
+                                               kl_side, kl_sync)
+
+        # decoder MLP over all N = B*HW objects at once (reference models.py:474-481)
         dec = self.object_decoder
         linears = [m for m in dec if isinstance(m, nn.Linear)]
         decoded = ops.USE_TENSOR_CORE_GEMM and len(linears) == 3 and linears[1].in_features % 4 == 0 \
@@ -266,7 +272,8 @@ class SPAIR(nn.Module):
             logits = ops.WideLinearFunction.apply(hidden, dec[-1].weight, dec[-1].bias)
         recon_x, recon_loss, _ = ops.RenderFunction.apply(logits, z_where.reshape(B * HW, 4), depth.reshape(-1),
                                                           pres.reshape(-1), x, B, HW, C, plan.G, Ih, Iw, c.scales, decoded)
-        kl_sums, kl_map = ops.KLFunction.apply(dmean, dstd, pres, plan.prior_mean, plan.prior_std, count_dist0, c.n_attr)
+        if "done" in kl_sync:
+            torch.cuda.current_stream(dev).wait_event(kl_sync["done"])
         kl_means = kl_sums.mean(dim=0)                       # batch mean of per-image sums (models.py:553)
         loss = recon_loss + (c.beta * self.kl_scale) * kl_means.sum()   # models.py:558
 

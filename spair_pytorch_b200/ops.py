@@ -169,14 +169,27 @@ class KLFunction(torch.autograd.Function):
     plus the non-differentiable kl_map [B,HW,D+1] for inspection."""
 
     @staticmethod
-    def forward(ctx, dmean, dstd, pres, prior_mean, prior_std, count_dist0, A):
+    def forward(ctx, dmean, dstd, pres, prior_mean, prior_std, count_dist0, A, side=None, sync=None):
+        """``side`` (a CUDA stream) + ``sync`` (dict): the kernel — a serial scan over the cells, one CTA per image, i.e.
+        pure latency on B of the 148 SMs — is launched on ``side`` so that it overlaps the decoder GEMMs and the renderer;
+        ``sync['done']`` is the event the consumer of the outputs must wait for.  Outputs are allocated on the current
+        stream (they belong to its allocator pool); CUDA-graph capture records the fork / join as a parallel branch."""
         dmean, dstd, pres = _c(dmean), _c(dstd), _c(pres)
         B, HW, D = dmean.shape
         dev = dmean.device
         kl_map = torch.empty(B, HW, D + 1, device=dev, dtype=torch.float32)
         p_z = torch.empty(B, HW, device=dev, dtype=torch.float32)
         sums = torch.empty(B, 7, device=dev, dtype=torch.float32)
-        K.kl_fwd(dmean, dstd, pres, prior_mean, prior_std, count_dist0, B, HW, A, kl_map, p_z, sums)
+        if side is None:
+            K.kl_fwd(dmean, dstd, pres, prior_mean, prior_std, count_dist0, B, HW, A, kl_map, p_z, sums)
+        else:
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream(dev))
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                K.kl_fwd(dmean, dstd, pres, prior_mean, prior_std, count_dist0, B, HW, A, kl_map, p_z, sums)
+                sync["done"] = torch.cuda.Event()
+                sync["done"].record(side)
         ctx.save_for_backward(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z)
         ctx.A = A
         ctx.mark_non_differentiable(kl_map)
@@ -188,7 +201,7 @@ class KLFunction(torch.autograd.Function):
         B, HW, _ = dmean.shape
         d_dmean, d_dstd, d_pres = torch.empty_like(dmean), torch.empty_like(dstd), torch.empty_like(pres)
         K.kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, _c(d_sums), B, HW, ctx.A, d_dmean, d_dstd, d_pres)
-        return d_dmean, d_dstd, d_pres, None, None, None, None
+        return d_dmean, d_dstd, d_pres, None, None, None, None, None, None
 
 
 # ==========================================================================================
