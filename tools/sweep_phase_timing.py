@@ -31,8 +31,10 @@ def main():
     lib = K.lib()
     if not hasattr(lib, "spair_debug_sweep_timing"):
         raise SystemExit("library was built without -DSW_TIMING (see the module docstring)")
-    net = helpers.build_model('A').cuda()
-    x = torch.rand(256, 1, 128, 128, device='cuda')
+    name = sys.argv[1] if len(sys.argv) > 1 else 'A'          # config (A / C / D) and batch: `... sweep_phase_timing.py C 64`
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    net = helpers.build_model(name).cuda()
+    x = torch.rand(batch, *net.image_shape, device='cuda')
     buf = (ctypes.c_longlong * 64)()
     for _ in range(3):
         net(x, 1000)[0].backward()
