@@ -5,12 +5,14 @@ Same constructor, ``forward(x, global_step=0) -> (loss, recon_x, z_where, z_pres
 unchanged.  Building the model under the same ``torch.manual_seed`` gives bit-identical
 parameters (modules are created in the reference's order and consume the same RNG stream).
 
-What runs where:
-  * backbone convs, the four per-cell MLPs and the decoder MLP: cuDNN / cuBLAS (dense contractions);
-  * everything else — lateral context, latent heads (reparameterisation, relaxed Bernoulli, box
-    decode), glimpse extraction, the fused decoder-renderer with BCE, the KL terms with the
-    count-prior scan — hand-written sm_100a kernels behind the C-ABI of include/spair_b200.h,
-    forward and backward (``ops.py``).  There is no CPU path: tensors must be CUDA fp32.
+What runs where (everything behind the C-ABI of include/spair_b200.h, forward and backward, ``ops.py``):
+  * the whole cell loop — lateral context, the four per-cell MLPs, latent heads (reparameterisation, relaxed
+    Bernoulli, box decode), glimpse extraction — one persistent sm_100a kernel per direction (csrc/sweep.cu);
+  * every other dense contraction — the decoder MLP (with the texel sigmoids in its epilogue), the weight gradients
+    of all MLPs, the backbone convolutions after the stem — the tcgen05 GEMM of csrc/gemm.cu (3xTF32 = fp32 accuracy);
+  * the fused renderer with BCE, the KL terms with the count-prior scan, the backbone stem — their own kernels.
+  No cuDNN / cuBLAS kernel runs in a step (``SPAIR_NO_TC_GEMM=1`` restores the library path for A/B comparisons).
+  There is no CPU path: tensors must be CUDA fp32.
 
 The per-cell loop of the reference (121 strictly sequential iterations, ~27k tiny ATen ops and
 ~1300 device->host syncs per forward) becomes Wc + 2(Hc-1) wavefronts with no host sync.

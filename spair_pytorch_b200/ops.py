@@ -1,8 +1,8 @@
 """Autograd wrappers and the wavefront sweep over the sm_100a kernels (host orchestration).
 
-Nothing here computes on the CPU: every numerical step is either a call into
-``libspair_b200.so`` (``kernels.py``) or a cuBLAS GEMM issued through ``torch.mm/addmm`` on
-preallocated device buffers.  The backward passes are written out by hand instead of taped:
+Nothing here computes on the CPU: every numerical step is a call into ``libspair_b200.so`` (``kernels.py``) — including
+the dense contractions, which run on the tcgen05 GEMM (``K.gemm3x``); ``torch.mm/addmm`` (cuBLAS) is only reached with
+``SPAIR_NO_TC_GEMM=1`` or on the per-wavefront fallback path.  The backward passes are written out by hand instead of taped:
 
   * ``GlimpseFunction`` / ``PasteFunction`` — ``stn()`` both directions (reference modules.py:216-273);
   * ``RenderFunction``  — fused decode + inverse warp + compositing (+ BCE) (models.py:481-547);
@@ -319,7 +319,8 @@ class DecoderFunction(torch.autograd.Function):
     bias + scale + sigmoid in its epilogue, so the [N, G*G*(C+1)] logits (194 MB at the default config) never reach HBM:
     the output is the texel records ``RenderFunction(decoded=True)`` consumes.  Backward takes the gradient wrt the RAW
     logits (that is what ``RenderFunction.backward`` returns in decoded mode) and runs dgrad / wgrad on the same kernel.
-    The first layer (K = A = 50: rows are not 16-byte multiples, so no TMA) is 3 % of the FLOPs and stays on cuBLAS."""
+    The first layer's K = A = 50 columns are 200-byte rows, which TMA cannot address: its input and weight are copied to
+    zero-padded buffers with a 16-byte row pitch (6 MB), so all three layers run on the tensor cores."""
 
     @staticmethod
     def forward(ctx, attr, w0, b0, w1, b1, w2, b2, period, scales):
