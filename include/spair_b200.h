@@ -380,6 +380,15 @@ int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb,
                      the ReLU takes the exact branch (the reference's gradient below the layer depends on it); NULL / 0: off */,
                  void* stream);
 
+/* Implicit-GEMM convolution of the backbone tail on a channels-last input x [B,H,W,C] (k x k window, stride s, no
+ * padding; reference modules.py:44-66), the patch matrix read tile by tile with TMA im2col loads instead of being
+ * materialised:  mode 1 (forward)  out[B*Ho*Wo, Cout] = act(patches(x) . other^T + bias), other = weight [Cout][(kh,kw,c)];
+ *                mode 2 (weight gradient)  out[Cout][(kh,kw,c)] = other^T . patches(x), other = dy [B*Ho*Wo, Cout].
+ * C must be a multiple of 32.  epilogue / workspace / splits / kink_ws as in spair_gemm3x. */
+int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int stride, int mode, const float* other,
+                      int ld_other, float* out, int ldc, int Cout, const float* bias, int epilogue, float* workspace,
+                      int splits, unsigned* kink_ws, int kink_cap, void* stream);
+
 /* Patch gather / transposed gather around spair_gemm3x for the k x k / stride s convolutions of the backbone tail
  * (reference modules.py:44-66), channels-last activations.  col[m][(kh*k + kw)*C + c] = x[b][s*oy+kh][s*ox+kw][c] with
  * m = (b*Ho + oy)*Wo + ox, Ho = (H-k)/s + 1 (no padding: the Backbone pads once, before the stem);

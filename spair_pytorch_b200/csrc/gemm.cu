@@ -61,6 +61,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  "l"(map), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+// TMA im2col load (4-D NHWC tensor map created by cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive output pixels
+// starting at input-space base (w, h) of image n, traversed with the convolution stride inside the map's bounding box,
+// 32 channels from channel c, at filter tap offset (off_w, off_h).  Lands as [pixel][32 channels] rows of 128 bytes.
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                int off_w, int off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+        : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -115,6 +125,10 @@ struct Params {
     float s_colour, s_alpha, b_alpha;
     int debug;            // diagnostics (SPAIR_GEMM_DEBUG): 1 = splitters skip their work, 2 = one MMA per k-step, 4 = no stores
     int acc_split;        // 1, or 4 (BN <= 128): k-block j accumulates into TMEM accumulator j % 4, summed in the epilogue
+    // implicit-GEMM convolution on a channels-last input (reference Backbone, modules.py:44-66): 0 = plain GEMM;
+    // 1 = the A operand is the patch matrix of x, read by TMA im2col (forward, rows = output pixels);
+    // 2 = the B operand is the patch matrix (weight gradient, reduction over the output pixels)
+    int conv, cv_Ho, cv_Wo, cv_k, cv_s, cv_cpb;   // output grid, kernel side, stride, 32-channel blocks per tap
     unsigned* kink_ws;    // ReLU sign fix-up list: [0] = counter, [1 .. kink_cap] = row * N + col of uncertain outputs
     int kink_cap;
 };
@@ -203,15 +217,33 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const int kb_n = k_blocks_of(sp), k_base = sp * p.k_per_split;
                 for (int kb = 0; kb < kb_n; ++kb) {
                     mbar_wait(bar_empty(stage), phase ^ 1);
-                    mbar_expect_tx(bar_full(stage), C::kStageA + C::kStageB);
+                    // (weight gradient of a convolution: a last column tile may hold fewer than BN / 32 patch atoms)
+                    const int b_atoms = p.conv == 2 ? min(BN / 32, (p.N - nt * BN + 31) / 32) : BN / 32;
+                    mbar_expect_tx(bar_full(stage), C::kStageA + (p.conv == 2 ? b_atoms * 4096 : C::kStageB));
                     const int k0 = k_base + kb * BK;
-                    if (A_K) {
+                    if (p.conv == 1) {
+                        // k-block -> (tap, 32-channel block); tile row 0 -> (image, oy, ox); 128 pixels in one instruction
+                        const int kbg = k0 / BK, tap = kbg / p.cv_cpb, cg = kbg - tap * p.cv_cpb;
+                        const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
+                        const int m0 = mt * BM, ox = m0 % p.cv_Wo, t = m0 / p.cv_Wo, oy = t % p.cv_Ho, n = t / p.cv_Ho;
+                        tma_load_im2col(a_hi(stage), &map_a, bar_full(stage), cg * 32, ox * p.cv_s, oy * p.cv_s, n, kw, kh);
+                    } else if (A_K) {
                         tma_load_2d(a_hi(stage), &map_a, bar_full(stage), k0, mt * BM);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(stage) + j * 4096, &map_a, bar_full(stage), mt * BM + 32 * j, k0);
                     }
-                    if (B_K) {
+                    if (p.conv == 2) {
+                        // 32 output pixels (the k-block) x BN / 32 (tap, channel block) atoms of the patch matrix
+                        const int ox = k0 % p.cv_Wo, t = k0 / p.cv_Wo, oy = t % p.cv_Ho, n = t / p.cv_Ho;
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) {
+                            if (j >= b_atoms) break;
+                            const int colg = nt * (BN / 32) + j, tap = colg / p.cv_cpb, cg = colg - tap * p.cv_cpb;
+                            const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
+                            tma_load_im2col(b_hi(stage) + j * 4096, &map_b, bar_full(stage), cg * 32, ox * p.cv_s, oy * p.cv_s, n, kw, kh);
+                        }
+                    } else if (B_K) {
                         tma_load_2d(b_hi(stage), &map_b, bar_full(stage), k0, nt * BN);
                     } else {
 #pragma unroll
@@ -454,6 +486,33 @@ __global__ void __launch_bounds__(256) relu_fixup_kernel(const float* __restrict
     }
 }
 
+// The same for an implicit-GEMM convolution: the patch row of output pixel m is gathered from the channels-last input.
+__global__ void __launch_bounds__(256) relu_fixup_conv_kernel(const float* __restrict__ x, int H, int W, int Cin, int k, int s, int Ho, int Wo,
+                                                              const float* __restrict__ w, int ldw, const float* __restrict__ bias,
+                                                              float* __restrict__ C, int ldc, int N, const unsigned* __restrict__ kink_ws, int cap) {
+    const unsigned count = min(kink_ws[0], (unsigned)cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
+        const unsigned idx = kink_ws[1 + e];
+        const unsigned m = idx / (unsigned)N, n = idx - m * (unsigned)N;
+        const int ox = (int)(m % (unsigned)Wo), t = (int)(m / (unsigned)Wo), oy = t % Ho, b = t / Ho;
+        const float* wr = w + (size_t)n * ldw;
+        double acc = 0.0;
+        for (int tap = 0; tap < k * k; ++tap) {
+            const int kh = tap / k, kw = tap - kh * k;
+            const float* xp = x + (((size_t)b * H + (size_t)s * oy + kh) * W + (size_t)s * ox + kw) * Cin;
+            for (int c = lane; c < Cin; c += 32) acc += (double)xp[c] * (double)wr[tap * Cin + c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            if (bias) acc += (double)bias[n];
+            C[(size_t)m * ldc + n] = acc > 0.0 ? (float)acc : 0.0f;
+        }
+    }
+}
+
 // C[m][n] = sum_s ws[s][m][n] (+ bias[n]), fixed order.
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long mn, int N, const float* __restrict__ bias,
                                      float* __restrict__ C, int ldc) {
@@ -492,6 +551,35 @@ static bool make_map(CUtensorMap* map, const float* ptr, int inner, int outer, i
     cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn encode_im2col_fn() {
+    static EncodeIm2colFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeIm2colFn>(f);
+    }();
+    return fn;
+}
+
+// channels-last x [B][H][W][C]; k x k window, stride s, no padding: base pixels live in [0, W - (k - 1)) x [0, H - (k - 1)),
+// the filter tap is added by the instruction's offsets.  32 channels x `pixels` output pixels per load.
+static bool make_im2col_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int k, int s, int pixels, bool kmajor_tile) {
+    EncodeIm2colFn fn = encode_im2col_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    int lower[2] = {0, 0}, upper[2] = {-(k - 1), -(k - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower, upper, 32, (cuuint32_t)pixels, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor_tile ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, bool A_K, bool B_K>
@@ -566,6 +654,7 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
     p.epilogue = epilogue;
     p.period = period;
     p.s_colour = s_colour; p.s_alpha = s_alpha; p.b_alpha = b_alpha;
+    p.conv = 0; p.cv_Ho = p.cv_Wo = p.cv_k = p.cv_s = p.cv_cpb = 1;
     // forward layers with a long reduction whose ReLU decisions matter: split accumulators (see the MMA warp)
     p.acc_split = (epilogue == SPAIR_GEMM_EPI_RELU && bn <= 128 && splits == 1 && K >= 512) ? 4 : 1;
     const bool fixup = kink_ws != nullptr && kink_cap > 0 && epilogue == SPAIR_GEMM_EPI_RELU;
@@ -593,5 +682,76 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
     if (rc != 0 || splits == 1) return rc;
     const long long mn = (long long)M * N;
     gemm::splitk_reduce_kernel<<<grid_for(mn, 256) < 4 * kSMs ? grid_for(mn, 256) : 4 * kSMs, 256, 0, st>>>(workspace, splits, mn, N, bias, C, ldc);
+    SPAIR_LAUNCH_CHECK();
+}
+
+// Implicit-GEMM convolution of the backbone tail (reference modules.py:44-66) on a channels-last input, no patch matrix in HBM:
+//   mode 1 (forward)         y[B*Ho*Wo, Cout] = act(patches(x) . w^T + bias),  w = [Cout][(kh, kw, c)]
+//   mode 2 (weight gradient) dw[Cout][(kh, kw, c)] = dy^T . patches(x),        dy = [B*Ho*Wo, Cout]
+// patches(x)[m][(kh*k + kw)*C + c] = x[b][s*oy + kh][s*ox + kw][c] is read tile by tile with TMA im2col loads.
+extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int stride, int mode, const float* other,
+                                 int ld_other, float* out, int ldc, int Cout, const float* bias, int epilogue, float* workspace,
+                                 int splits, unsigned* kink_ws, int kink_cap, void* stream) {
+    SPAIR_REQUIRE(x && other && out && B > 0 && H >= k && W >= k && C > 0 && (C & 31) == 0 && k > 0 && k <= 8 && stride > 0 && stride <= 8);
+    SPAIR_REQUIRE((mode == 1 || mode == 2) && Cout > 0 && splits >= 1 && (ld_other & 3) == 0);
+    SPAIR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)other & 15) == 0);
+    const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+    const long long pixels = (long long)B * Ho * Wo;
+    SPAIR_REQUIRE(pixels < (1ll << 31));
+    const int KK = k * k * C;
+    gemm::Params p;
+    CUtensorMap ma, mb;
+    int bn;
+    bool ok;
+    if (mode == 1) {
+        SPAIR_REQUIRE(epilogue == SPAIR_GEMM_EPI_NONE || epilogue == SPAIR_GEMM_EPI_RELU);
+        SPAIR_REQUIRE(splits == 1);
+        p.M = (int)pixels; p.N = Cout; p.K = KK;
+        bn = spair_gemm_block_n(p.N, 1);
+        ok = gemm::make_im2col_map(&ma, x, B, H, W, C, k, stride, gemm::BM, true) && gemm::make_map(&mb, other, KK, Cout, ld_other, gemm::BK, bn, true);
+    } else {
+        SPAIR_REQUIRE(epilogue == SPAIR_GEMM_EPI_NONE && bias == nullptr && (splits == 1 || workspace != nullptr));
+        p.M = Cout; p.N = KK; p.K = (int)pixels;
+        bn = spair_gemm_block_n(p.N, 0);
+        ok = gemm::make_map(&ma, other, Cout, (int)pixels, ld_other, 32, gemm::BK, false) && gemm::make_im2col_map(&mb, x, B, H, W, C, k, stride, 32, false);
+    }
+    SPAIR_REQUIRE(ok);
+    const int kb_total = (p.K + gemm::BK - 1) / gemm::BK;
+    const int kb_per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kb_per - 1) / kb_per;
+    p.splits = splits;
+    p.k_per_split = kb_per * gemm::BK;
+    p.C = splits == 1 ? out : workspace;
+    p.ldc = splits == 1 ? ldc : p.N;
+    p.bias = bias;
+    p.epilogue = epilogue;
+    p.period = 2; p.s_colour = p.s_alpha = 1.0f; p.b_alpha = 0.0f;
+    p.conv = mode; p.cv_Ho = Ho; p.cv_Wo = Wo; p.cv_k = k; p.cv_s = stride; p.cv_cpb = C / 32;
+    p.acc_split = (mode == 1 && epilogue == SPAIR_GEMM_EPI_RELU && bn <= 128 && p.K >= 512) ? 4 : 1;
+    const bool fixup = mode == 1 && kink_ws != nullptr && kink_cap > 0 && epilogue == SPAIR_GEMM_EPI_RELU && (long long)p.M * p.N < (1ll << 32);
+    p.kink_ws = fixup ? kink_ws : nullptr;
+    p.kink_cap = kink_cap;
+    const char* dbg = getenv("SPAIR_GEMM_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool a_k = mode == 1, b_k = mode == 1;
+    if (fixup) {
+        cudaError_t e = cudaMemsetAsync(kink_ws, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int rc;
+    switch (bn) {
+        case 224: rc = gemm::launch_major<224>(a_k, b_k, ma, mb, p, st); break;
+        case 256: rc = gemm::launch_major<256>(a_k, b_k, ma, mb, p, st); break;
+        case 128: rc = gemm::launch_major<128>(a_k, b_k, ma, mb, p, st); break;
+        default: rc = gemm::launch_major<64>(a_k, b_k, ma, mb, p, st); break;
+    }
+    if (rc == 0 && fixup) {
+        gemm::relu_fixup_conv_kernel<<<2 * kSMs, 256, 0, st>>>(x, H, W, C, k, stride, Ho, Wo, other, ld_other, bias, out, ldc, Cout, kink_ws, kink_cap);
+        SPAIR_LAUNCH_CHECK();
+    }
+    if (rc != 0 || splits == 1) return rc;
+    const long long mn = (long long)p.M * p.N;
+    gemm::splitk_reduce_kernel<<<grid_for(mn, 256) < 4 * kSMs ? grid_for(mn, 256) : 4 * kSMs, 256, 0, st>>>(workspace, splits, mn, p.N, nullptr, out, ldc);
     SPAIR_LAUNCH_CHECK();
 }

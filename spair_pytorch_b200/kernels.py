@@ -89,6 +89,7 @@ _SIGNATURES = {
     "spair_gemm_block_n": [_I, _I],
     "spair_gemm_splits": [_I, _I, _I],
     "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P],
+    "spair_conv_gemm3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P],
     "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_transpose_batched": [_P, _I, _I, _I, _P, _P],
@@ -442,6 +443,37 @@ def relu_bwd_colsum(g, y, out):
     LAUNCH_COUNT += 1
 
 
+def conv_supported(x, k: int, stride: int) -> bool:
+    """Shapes the TMA-im2col convolution (spair_conv_gemm3x) covers: channels-last fp32, C % 32 == 0, k, stride <= 8."""
+    return x.dim() == 4 and x.is_contiguous() and x.shape[3] % 32 == 0 and 1 <= k <= 8 and 1 <= stride <= 8 and x.data_ptr() % 16 == 0
+
+
+def conv_fwd(x, k: int, stride: int, wr, bias, out, relu: bool, exact_relu=True):
+    """out[B*Ho*Wo, Cout] = act(patches(x) . wr^T + bias): x [B,H,W,C] channels-last, wr [Cout, k*k*C] in (kh, kw, c) order."""
+    B, H, W, C = x.shape
+    fix = relu and exact_relu and out.numel() < (1 << 32)
+    kink = _kink_workspace(out.device) if fix else None
+    _check(lib().spair_conv_gemm3x(_ptr(_contig(x, "x")), B, H, W, C, k, stride, 1, _ptr(wr), _ld(wr), _ptr(out), _ld(out),
+                                   wr.shape[0], _ptr(bias), GEMM_EPI_RELU if relu else GEMM_EPI_NONE, None, 1,
+                                   kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _stream()), "spair_conv_gemm3x")
+    if fix:
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+
+
+def conv_wgrad(x, k: int, stride: int, dy, d_wr):
+    """d_wr[Cout, k*k*C] = dy^T . patches(x): dy [B*Ho*Wo, Cout]; deterministic split over the pixels."""
+    B, H, W, C = x.shape
+    Cout, KK = d_wr.shape
+    splits = lib().spair_gemm_splits(Cout, KK, dy.shape[0])
+    ws = _gemm_workspace(d_wr.device, splits * Cout * KK) if splits > 1 else None
+    _check(lib().spair_conv_gemm3x(_ptr(_contig(x, "x")), B, H, W, C, k, stride, 2, _ptr(dy), _ld(dy), _ptr(d_wr), _ld(d_wr),
+                                   Cout, None, GEMM_EPI_NONE, _ptr(ws), splits, None, 0, _stream()), "spair_conv_gemm3x")
+    if splits > 1:
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+
+
 def im2col_nhwc(x, k: int, stride: int, col):
     """x [B,H,W,C] channels-last -> col [B*Ho*Wo, k*k*C] (see spair_im2col_nhwc)."""
     B, H, W, C = x.shape
@@ -614,6 +646,6 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
 # device guard on every launch wrapper (see _device_guarded)
 for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
               "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
-              "sweep_bwd", "gemm3x", "im2col_nhwc", "col2im_nhwc", "transpose_batched", "relu_bwd_colsum", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+              "sweep_bwd", "gemm3x", "conv_fwd", "conv_wgrad", "im2col_nhwc", "col2im_nhwc", "transpose_batched", "relu_bwd_colsum", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
     globals()[_name] = _device_guarded(globals()[_name])
 del _name

@@ -32,6 +32,9 @@ SWEEP_EVENTS: Optional[dict] = None
 # reference the tensor-core path is tested against)
 import os as _os
 USE_TENSOR_CORE_GEMM = "SPAIR_NO_TC_GEMM" not in _os.environ
+# k x k convolutions of the backbone tail as implicit GEMMs (TMA im2col loads in the GEMM's producer warp) instead of a
+# materialised patch matrix; SPAIR_EXPLICIT_IM2COL=1 restores the explicit path (csrc/conv.cu im2col_nhwc)
+IMPLICIT_CONV = "SPAIR_EXPLICIT_IM2COL" not in _os.environ
 
 
 def _timed_launch(name, fn, *args):
@@ -422,9 +425,9 @@ class ConvTailFunction(torch.autograd.Function):
 
     cuDNN has no fp32-accurate tensor-core convolution (TF32 is off for parity), so the library path runs these layers
     on the fp32 SIMT / FFT engines at ~20 TFLOP/s — 8 of the 16.4 ms of a config-B step.  Here the activations are kept
-    channels-last, a 1x1 layer is a GEMM on the stored tensor, a k x k / stride s layer a GEMM on its patch matrix
-    (csrc/conv.cu), bias + ReLU run in the GEMM epilogue, and the backward is dgrad / wgrad on the same kernel plus the
-    transposed patch gather.  Layers: padding 0, dilation 1, groups 1, square kernel, Cin % 4 == 0.
+    channels-last, a 1x1 layer is a GEMM on the stored tensor, a k x k / stride s layer an implicit GEMM whose producer
+    warp reads the patches with TMA im2col loads (forward and weight gradient; no patch matrix in HBM), bias + ReLU run in
+    the GEMM epilogue, and the input gradient is dgrad on the same kernel plus the transposed patch gather (csrc/conv.cu).  Layers: padding 0, dilation 1, groups 1, square kernel, Cin % 4 == 0.
 
     forward(y0 [B,C0,H0,W0] NCHW (the stem's output), specs, *weights_and_biases) -> feat [B,F,Hc,Wc] NCHW;
     ``specs`` = ((k, stride, relu), ...)."""
@@ -441,13 +444,17 @@ class ConvTailFunction(torch.autograd.Function):
             Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
             M = Bn * Ho * Wo
             wr = w.permute(0, 2, 3, 1).reshape(w.shape[0], k * k * Cin).contiguous()     # [Cout, (kh, kw, c)]
+            y = torch.empty(M, w.shape[0], device=x.device, dtype=torch.float32)
             if k == 1 and s == 1:
                 a = x.view(M, Cin)
+                K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
+            elif IMPLICIT_CONV and K.conv_supported(x, k, s):
+                a = x                                   # implicit GEMM: the producer warp reads the patches with TMA im2col
+                K.conv_fwd(x, k, s, wr, b, y, relu)
             else:
                 a = torch.empty(M, k * k * Cin, device=x.device, dtype=torch.float32)
                 K.im2col_nhwc(x, k, s, a)
-            y = torch.empty(M, w.shape[0], device=x.device, dtype=torch.float32)
-            K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
+                K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
             saved += [a, wr, y]
             shapes.append((Bn, H, W, Cin, Ho, Wo, tuple(w.shape)))
             x = y.view(Bn, Ho, Wo, w.shape[0])
@@ -472,12 +479,16 @@ class ConvTailFunction(torch.autograd.Function):
             db = torch.empty(wshape[0], device=dy.device, dtype=torch.float32)
             K.relu_bwd_colsum(dy, y if relu else None, db)            # ReLU mask (in place) + bias gradient, one pass
             d_wr = torch.empty_like(wr)
-            K.gemm3x(dy, False, a, False, d_wr)
+            implicit = a.dim() == 4                     # forward ran as an implicit GEMM: `a` is the channels-last input
+            if implicit:
+                K.conv_wgrad(a, k, s, dy, d_wr)
+            else:
+                K.gemm3x(dy, False, a, False, d_wr)
             grads[2 * li] = d_wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2).contiguous()
             grads[2 * li + 1] = db
             if li == 0 and not ctx.needs_input_grad[0]:
                 return (None, None) + tuple(grads)
-            da = torch.empty_like(a)
+            da = torch.empty(dy.shape[0], wr.shape[1], device=dy.device, dtype=torch.float32)
             K.gemm3x(dy, True, wr, False, da)
             if k == 1 and s == 1:
                 dy = da

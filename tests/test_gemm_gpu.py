@@ -227,3 +227,32 @@ def test_transpose_and_relu_bwd_colsum():
         k_.relu_bwd_colsum(b, y, o2)
         assert torch.equal(a, want_g) and torch.equal(o1, o2)
         assert_close(o1, want.float(), "column sums", atol=1e-5 + 1e-6 * float(want_g.abs().sum(0).max()))
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,k,s", [(1, 10, 10, 32, 64, 4, 2), (2, 9, 11, 64, 128, 3, 1), (3, 50, 50, 128, 128, 4, 2),
+                                              (5, 24, 24, 128, 100, 4, 2)])
+def test_implicit_conv_matches_explicit_patches(B, H, W, C, Cout, k, s):
+    """spair_conv_gemm3x (TMA im2col loads inside the GEMM's producer warp) against the materialised patch matrix in float64:
+    forward with bias + ReLU (rows = output pixels, tiles spanning image rows and images, ragged last tile) and the weight
+    gradient (reduction over the pixels, split-K, partial column tiles)."""
+    k_ = K()
+    g = torch.Generator(device=DEV).manual_seed(B * 31 + H)
+    x = torch.randn(B, H, W, C, device=DEV, generator=g)
+    w = torch.randn(Cout, k * k * C, device=DEV, generator=g) * 0.05
+    b = torch.randn(Cout, device=DEV, generator=g)
+    Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+    M = B * Ho * Wo
+    col = torch.empty(M, k * k * C, device=DEV)
+    k_.im2col_nhwc(x, k, s, col)
+    pre = col.double() @ w.double().t() + b.double()
+    y = torch.full((M, Cout), float("nan"), device=DEV)
+    k_.conv_fwd(x, k, s, w, b, y, relu=True)
+    scale = col.double().abs() @ w.double().abs().t() + b.double().abs()
+    assert ((y.double() - pre.clamp_min(0)).abs() / scale).max().item() < 5e-6
+    assert torch.equal(y > 0, pre > 0)                 # the exact-sign fix-up: every ReLU branch is the float64 one
+    dy = torch.randn(M, Cout, device=DEV, generator=g)
+    dw = torch.full((Cout, k * k * C), float("nan"), device=DEV)
+    k_.conv_wgrad(x, k, s, dy, dw)
+    ref = dy.double().t() @ col.double()
+    scale = dy.double().abs().t() @ col.double().abs()
+    assert ((dw.double() - ref).abs() / scale).max().item() < 5e-6
