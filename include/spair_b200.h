@@ -389,6 +389,14 @@ int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int str
                       int ld_other, float* out, int ldc, int Cout, const float* bias, int epilogue, float* workspace,
                       int splits, unsigned* kink_ws, int kink_cap, void* stream);
 
+/* Input gradient of the same convolution (k % stride == 0, Cout % 32 == 0) without a d_col matrix: stride*stride stride-1
+ * sub-convolutions over dy (one GEMM per output parity class; the epilogue scatters the rows to their pixels of dx).
+ * dy [B,Ho,Wo,Cout] channels-last; wc: the stride*stride packed class weights [Cin][T*T*Cout], T = k / stride,
+ * wc[py*stride+px][c][(kh*T + kw)*Cout + co] = w[co][c][py + stride*(T-1-kh)][px + stride*(T-1-kw)];
+ * dx [B,H,W,Cin] is fully overwritten. */
+int spair_conv_dgrad3x(const float* dy, int B, int H, int W, int Cin, int k, int stride, int Cout, const float* wc,
+                       float* dx, void* stream);
+
 /* Patch gather / transposed gather around spair_gemm3x for the k x k / stride s convolutions of the backbone tail
  * (reference modules.py:44-66), channels-last activations.  col[m][(kh*k + kw)*C + c] = x[b][s*oy+kh][s*ox+kw][c] with
  * m = (b*Ho + oy)*Wo + ox, Ho = (H-k)/s + 1 (no padding: the Backbone pads once, before the stem);

@@ -129,6 +129,10 @@ struct Params {
     // 1 = the A operand is the patch matrix of x, read by TMA im2col (forward, rows = output pixels);
     // 2 = the B operand is the patch matrix (weight gradient, reduction over the output pixels)
     int conv, cv_Ho, cv_Wo, cv_k, cv_s, cv_cpb;   // output grid, kernel side, stride, 32-channel blocks per tap
+    int cv_base;          // input-space coordinate of output pixel 0's window (0; -(T-1) for the transposed convolution)
+    // input gradient of a strided convolution as s*s stride-1 sub-convolutions over dy (one per output parity class): GEMM
+    // row m = (b*cv_Ho + i)*cv_Wo + j is pixel (s*i + py, s*j + px) of dx [B, om_H, om_W, N]; om_s = 0: rows are stored as is
+    int om_s, om_H, om_W, om_py, om_px;
     unsigned* kink_ws;    // ReLU sign fix-up list: [0] = counter, [1 .. kink_cap] = row * N + col of uncertain outputs
     int kink_cap;
 };
@@ -226,7 +230,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const int kbg = k0 / BK, tap = kbg / p.cv_cpb, cg = kbg - tap * p.cv_cpb;
                         const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
                         const int m0 = mt * BM, ox = m0 % p.cv_Wo, t = m0 / p.cv_Wo, oy = t % p.cv_Ho, n = t / p.cv_Ho;
-                        tma_load_im2col(a_hi(stage), &map_a, bar_full(stage), cg * 32, ox * p.cv_s, oy * p.cv_s, n, kw, kh);
+                        tma_load_im2col(a_hi(stage), &map_a, bar_full(stage), cg * 32, ox * p.cv_s + p.cv_base, oy * p.cv_s + p.cv_base, n, kw, kh);
                     } else if (A_K) {
                         tma_load_2d(a_hi(stage), &map_a, bar_full(stage), k0, mt * BM);
                     } else {
@@ -433,7 +437,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(stg + (rr * kStgPitch + cc) * 4));
                         const int grow = row0 + rr;
                         if (grow < p.M) {
-                            float* dst = cbase + (size_t)grow * p.ldc + col;
+                            size_t orow = (size_t)grow;
+                            if (p.om_s) {      // parity-class row -> pixel of the full-resolution gradient map
+                                const int j = grow % p.cv_Wo, t = grow / p.cv_Wo, i = t % p.cv_Ho, b = t / p.cv_Ho;
+                                orow = ((size_t)b * p.om_H + (size_t)p.om_s * i + p.om_py) * p.om_W + (size_t)p.om_s * j + p.om_px;
+                            }
+                            float* dst = cbase + orow * p.ldc + col;
                             if (vec_ok && col + 4 <= p.N) {
                                 *reinterpret_cast<float4*>(dst) = o;
                             } else {
@@ -570,12 +579,13 @@ static EncodeIm2colFn encode_im2col_fn() {
 
 // channels-last x [B][H][W][C]; k x k window, stride s, no padding: base pixels live in [0, W - (k - 1)) x [0, H - (k - 1)),
 // the filter tap is added by the instruction's offsets.  32 channels x `pixels` output pixels per load.
-static bool make_im2col_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int k, int s, int pixels, bool kmajor_tile) {
+static bool make_im2col_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int k, int s, int pixels, bool kmajor_tile,
+                            int lower_w = 0, int lower_h = 0, int upper_w = 1 << 30, int upper_h = 1 << 30) {
     EncodeIm2colFn fn = encode_im2col_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    int lower[2] = {0, 0}, upper[2] = {-(k - 1), -(k - 1)};
+    int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w == (1 << 30) ? -(k - 1) : upper_w, upper_h == (1 << 30) ? -(k - 1) : upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower, upper, 32, (cuuint32_t)pixels, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor_tile ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -655,6 +665,7 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
     p.period = period;
     p.s_colour = s_colour; p.s_alpha = s_alpha; p.b_alpha = b_alpha;
     p.conv = 0; p.cv_Ho = p.cv_Wo = p.cv_k = p.cv_s = p.cv_cpb = 1;
+    p.cv_base = 0; p.om_s = p.om_H = p.om_W = p.om_py = p.om_px = 0;
     // forward layers with a long reduction whose ReLU decisions matter: split accumulators (see the MMA warp)
     p.acc_split = (epilogue == SPAIR_GEMM_EPI_RELU && bn <= 128 && splits == 1 && K >= 512) ? 4 : 1;
     const bool fixup = kink_ws != nullptr && kink_cap > 0 && epilogue == SPAIR_GEMM_EPI_RELU;
@@ -727,6 +738,7 @@ extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int
     p.epilogue = epilogue;
     p.period = 2; p.s_colour = p.s_alpha = 1.0f; p.b_alpha = 0.0f;
     p.conv = mode; p.cv_Ho = Ho; p.cv_Wo = Wo; p.cv_k = k; p.cv_s = stride; p.cv_cpb = C / 32;
+    p.cv_base = 0; p.om_s = p.om_H = p.om_W = p.om_py = p.om_px = 0;
     p.acc_split = (mode == 1 && epilogue == SPAIR_GEMM_EPI_RELU && bn <= 128 && p.K >= 512) ? 4 : 1;
     const bool fixup = mode == 1 && kink_ws != nullptr && kink_cap > 0 && epilogue == SPAIR_GEMM_EPI_RELU && (long long)p.M * p.N < (1ll << 32);
     p.kink_ws = fixup ? kink_ws : nullptr;
@@ -754,4 +766,49 @@ extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int
     const long long mn = (long long)p.M * p.N;
     gemm::splitk_reduce_kernel<<<grid_for(mn, 256) < 4 * kSMs ? grid_for(mn, 256) : 4 * kSMs, 256, 0, st>>>(workspace, splits, mn, p.N, nullptr, out, ldc);
     SPAIR_LAUNCH_CHECK();
+}
+
+// Input gradient of the same convolution without a d_col matrix: dx[b][s*i+py][s*j+px][c] = sum over the T x T taps (T = k / s)
+// of dy[b][i-a][j-a'][:] . w[:, c, py + s*a, px + s*a'] — s*s stride-1 sub-convolutions over dy (zero padded by T-1 through the
+// TMA bounding box), one GEMM per output parity class, whose rows the epilogue scatters to their pixels of dx.
+//   dy [B,Ho,Wo,Cout] channels-last (Cout % 32 == 0);  wc: s*s packed class weights [Cin][(a', a, co) = T*T*Cout] with
+//   wc[cls = py*s+px][c][((T-1-a)*T + (T-1-a'))*Cout + co] = w[co][c][py + s*a][px + s*a'];  dx [B,H,W,Cin] (fully overwritten).
+extern "C" int spair_conv_dgrad3x(const float* dy, int B, int H, int W, int Cin, int k, int stride, int Cout, const float* wc,
+                                  float* dx, void* stream) {
+    SPAIR_REQUIRE(dy && wc && dx && B > 0 && H >= k && W >= k && Cin > 0 && Cout > 0 && (Cout & 31) == 0 && k > 0 && stride > 0);
+    SPAIR_REQUIRE(k % stride == 0 && k / stride <= 8 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)wc & 15) == 0);
+    const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1, T = k / stride, KK = T * T * Cout;
+    // rows / columns of x beyond the last window receive no gradient: the caller gets zeros there from the class loop below
+    // only if every pixel belongs to some class row, i.e. Hp covers all of H
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bn = spair_gemm_block_n(Cin, 1);
+    for (int py = 0; py < stride; ++py)
+        for (int px = 0; px < stride; ++px) {
+            const int Hp = (H - py + stride - 1) / stride, Wp = (W - px + stride - 1) / stride;
+            if (Hp <= 0 || Wp <= 0) continue;
+            gemm::Params p;
+            p.M = B * Hp * Wp; p.N = Cin; p.K = KK;
+            p.splits = 1; p.k_per_split = ((KK + gemm::BK - 1) / gemm::BK) * gemm::BK;
+            p.C = dx; p.ldc = Cin; p.bias = nullptr; p.epilogue = SPAIR_GEMM_EPI_NONE;
+            p.period = 2; p.s_colour = p.s_alpha = 1.0f; p.b_alpha = 0.0f;
+            p.conv = 1; p.cv_Ho = Hp; p.cv_Wo = Wp; p.cv_k = T; p.cv_s = 1; p.cv_cpb = Cout / 32; p.cv_base = -(T - 1);
+            p.om_s = stride; p.om_H = H; p.om_W = W; p.om_py = py; p.om_px = px;
+            p.acc_split = 1; p.kink_ws = nullptr; p.kink_cap = 0;
+            const char* dbg = getenv("SPAIR_GEMM_DEBUG");
+            p.debug = dbg ? atoi(dbg) : 0;
+            CUtensorMap ma, mb;
+            // base positions of the T-wide window over dy: [-(T-1), Wp - (T-1)) -> upper corner = Wp - Wo - (T-1)
+            bool ok = gemm::make_im2col_map(&ma, dy, B, Ho, Wo, Cout, T, 1, gemm::BM, true, -(T - 1), -(T - 1), Wp - Wo - (T - 1), Hp - Ho - (T - 1));
+            ok = ok && gemm::make_map(&mb, wc + (size_t)(py * stride + px) * Cin * KK, KK, Cin, KK, gemm::BK, bn, true);
+            SPAIR_REQUIRE(ok);
+            int rc;
+            switch (bn) {
+                case 224: rc = gemm::launch_major<224>(true, true, ma, mb, p, st); break;
+                case 256: rc = gemm::launch_major<256>(true, true, ma, mb, p, st); break;
+                case 128: rc = gemm::launch_major<128>(true, true, ma, mb, p, st); break;
+                default: rc = gemm::launch_major<64>(true, true, ma, mb, p, st); break;
+            }
+            if (rc != 0) return rc;
+        }
+    return 0;
 }

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "spair_gemm_splits": [_I, _I, _I],
     "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P],
     "spair_conv_gemm3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P],
+    "spair_conv_dgrad3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_transpose_batched": [_P, _I, _I, _I, _P, _P],
@@ -474,6 +475,33 @@ def conv_wgrad(x, k: int, stride: int, dy, d_wr):
         LAUNCH_COUNT += 1
 
 
+def conv_dgrad_supported(k: int, stride: int, Cout: int) -> bool:
+    return k % stride == 0 and k // stride <= 8 and Cout % 32 == 0
+
+
+def pack_dgrad_weights(w, stride: int):
+    """w [Cout, Cin, k, k] -> the stride*stride class weights of spair_conv_dgrad3x, [s*s, Cin, T*T*Cout]."""
+    Cout, Cin, k, _ = w.shape
+    T = k // stride
+    classes = []
+    for py in range(stride):
+        for px in range(stride):
+            sub = w[:, :, py::stride, px::stride].flip(2, 3)               # [Cout, Cin, T, T] indexed [T-1-a][T-1-a']
+            classes.append(sub.permute(1, 2, 3, 0).reshape(Cin, T * T * Cout))
+    return torch.stack(classes).contiguous()
+
+
+def conv_dgrad(dy, B: int, k: int, stride: int, wc, dx):
+    """dx [B,H,W,Cin] = input gradient of the k x k / stride convolution; dy [B*Ho*Wo, Cout] channels-last rows."""
+    _, H, W, Cin = dx.shape
+    Cout = dy.shape[1]
+    n_cls = stride * stride
+    _check(lib().spair_conv_dgrad3x(_ptr(_contig(dy, "dy")), B, H, W, Cin, k, stride, Cout, _ptr(_contig(wc, "wc")),
+                                    _ptr(_contig(dx, "dx")), _stream()), "spair_conv_dgrad3x")
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += n_cls - 1
+
+
 def im2col_nhwc(x, k: int, stride: int, col):
     """x [B,H,W,C] channels-last -> col [B*Ho*Wo, k*k*C] (see spair_im2col_nhwc)."""
     B, H, W, C = x.shape
@@ -646,6 +674,6 @@ def kl_bwd(dmean, dstd, pres, prior_mean, prior_std, kl_map, p_z, d_sums, B, HW,
 # device guard on every launch wrapper (see _device_guarded)
 for _name in ("context_gather_fwd", "context_grad_gather", "box_head_fwd", "box_head_bwd", "normal_head_fwd", "normal_head_bwd",
               "pres_head_fwd", "pres_head_bwd", "relu_bwd", "stem_conv_fwd", "broadcast_rows", "stem_conv_bwd", "sweep_fwd",
-              "sweep_bwd", "gemm3x", "conv_fwd", "conv_wgrad", "im2col_nhwc", "col2im_nhwc", "transpose_batched", "relu_bwd_colsum", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
+              "sweep_bwd", "gemm3x", "conv_fwd", "conv_wgrad", "conv_dgrad", "im2col_nhwc", "col2im_nhwc", "transpose_batched", "relu_bwd_colsum", "glimpse_fwd", "glimpse_bwd", "paste_fwd", "paste_bwd", "render_fwd", "render_bwd", "kl_fwd", "kl_bwd"):
     globals()[_name] = _device_guarded(globals()[_name])
 del _name

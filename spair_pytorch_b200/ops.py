@@ -488,6 +488,13 @@ class ConvTailFunction(torch.autograd.Function):
             grads[2 * li + 1] = db
             if li == 0 and not ctx.needs_input_grad[0]:
                 return (None, None) + tuple(grads)
+            if implicit and K.conv_dgrad_supported(k, s, wshape[0]):
+                # transposed convolution as s*s implicit GEMMs over dy (no d_col matrix, no scatter pass)
+                w4 = wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2)
+                dx = torch.empty(Bn, H, W, Cin, device=dy.device, dtype=torch.float32)
+                K.conv_dgrad(dy, Bn, k, s, K.pack_dgrad_weights(w4, s), dx)
+                dy = dx.view(Bn * H * W, Cin)
+                continue
             da = torch.empty(dy.shape[0], wr.shape[1], device=dy.device, dtype=torch.float32)
             K.gemm3x(dy, True, wr, False, da)
             if k == 1 and s == 1:

@@ -256,3 +256,24 @@ def test_implicit_conv_matches_explicit_patches(B, H, W, C, Cout, k, s):
     ref = dy.double().t() @ col.double()
     scale = dy.double().abs().t() @ col.double().abs()
     assert ((dw.double() - ref).abs() / scale).max().item() < 5e-6
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", [(1, 10, 10, 32, 64, 4, 2), (3, 50, 50, 128, 128, 4, 2), (2, 24, 24, 128, 128, 4, 2),
+                                                (2, 13, 11, 16, 32, 4, 2), (2, 12, 12, 8, 32, 3, 3)])
+def test_implicit_conv_dgrad_matches_torch(B, H, W, Cin, Cout, k, s):
+    """spair_conv_dgrad3x (the input gradient as s*s implicit GEMMs over dy, rows scattered to their pixels by the epilogue)
+    against torch's conv2d backward in float64, incl. odd sizes whose last rows / columns no window reaches (zero gradient)."""
+    k_ = K()
+    g = torch.Generator(device=DEV).manual_seed(H * 7 + Cin)
+    w = torch.randn(Cout, Cin, k, k, device=DEV, generator=g) * 0.05
+    Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV, generator=g)
+    x64 = torch.zeros(B, Cin, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x64, w.double(), stride=s).backward(dy.permute(0, 3, 1, 2).double())
+    ref = x64.grad.permute(0, 2, 3, 1)
+    dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)
+    k_.conv_dgrad(dy.view(-1, Cout), B, k, s, k_.pack_dgrad_weights(w, s), dx)
+    assert not torch.isnan(dx).any()
+    scale = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double().abs(), w.double().abs(), stride=s)
+    scale = torch.nn.functional.pad(scale, (0, W - scale.shape[3], 0, H - scale.shape[2])).permute(0, 2, 3, 1) + 1e-30
+    assert ((dx.double() - ref).abs() / scale.clamp_min(1e-6)).max().item() < 5e-6
