@@ -329,31 +329,53 @@ __global__ void __launch_bounds__(kResThreads, 3) glimpse_resident_kernel(ResArg
                 const float bx = base_x[j];
                 const float4 cj = res_axis(bx, A.ax, A.cx, p.Iw, 1, col_m);
                 const int x0 = __float_as_int(cj.x), x1 = __float_as_int(cj.y);
+                // shared-memory byte addresses of the two tap columns (32-bit arithmetic, ld.shared) and a running output /
+                // gradient pointer: the loop body is 1 broadcast + 4 gathers + the interpolation + one coalesced access
+                const uint32_t img_s = g_smem_u32(img);
+                const uint32_t row_s = g_smem_u32(row);
                 for (int c = 0; c < p.C; ++c) {
-                    const float* pl = img + (size_t)c * plane;
-                    const size_t o_base = r * p.ld_out + (size_t)c * GG + j;
+                    const uint32_t a0 = img_s + 4u * (uint32_t)(c * plane + x0), a1 = img_s + 4u * (uint32_t)(c * plane + x1);
                     if (!lane_on) continue;
-#pragma unroll 7
-                    for (int i = sub; i < p.Gh; i += rpi) {
-                        float g = 0.0f;
-                        if (BWD) g = __ldg(p.d_out + o_base + (size_t)i * p.Gw);      // issued first: the HBM latency to hide
-                        const float4 ri = row[i];
-                        const int y0 = __float_as_int(ri.x), y1 = __float_as_int(ri.y);
-                        const float v00 = pl[y0 + x0], v01 = pl[y0 + x1], v10 = pl[y1 + x0], v11 = pl[y1 + x1];
-                        if (!BWD) {
-                            float a = __fmul_rn(v00, __fmul_rn(cj.z, ri.z));
-                            a = fmaf(v01, __fmul_rn(cj.w, ri.z), a);
-                            a = fmaf(v10, __fmul_rn(cj.z, ri.w), a);
-                            a = fmaf(v11, __fmul_rn(cj.w, ri.w), a);
-                            p.out[o_base + (size_t)i * p.Gw] = a;
-                        } else {
-                            // grid_sampler_2d_backward: d out / d ix, d out / d iy; zero where the coordinate was clamped
-                            const float dgx = g * ((v01 - v00) * ri.z + (v11 - v10) * ri.w) * col_m;
-                            const float dgy = g * ((v10 - v00) * cj.z + (v11 - v01) * cj.w) * row_m[i];
-                            acc[0] += dgx;
-                            acc[1] += dgy;
-                            acc[2] = fmaf(dgx, bx, acc[2]);
-                            acc[3] = fmaf(dgy, base_y[i], acc[3]);
+                    const size_t o_first = r * p.ld_out + (size_t)c * GG + j + (size_t)sub * p.Gw;
+                    float* op = BWD ? nullptr : p.out + o_first;
+                    const float* gp = BWD ? p.d_out + o_first : nullptr;
+                    const int step = rpi * p.Gw;
+                    constexpr int U = 7;      // rows per batch: the gradient loads of a whole batch are issued before its gathers
+                    for (int i0 = sub; i0 < p.Gh; i0 += U * rpi) {
+                        float g[U];
+                        if (BWD) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) g[u] = (i0 + u * rpi < p.Gh) ? __ldg(gp + (size_t)u * step) : 0.0f;
+                            gp += (size_t)U * step;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int i = i0 + u * rpi;
+                            if (i >= p.Gh) break;
+                            float4 ri;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ri.x), "=f"(ri.y), "=f"(ri.z), "=f"(ri.w) : "r"(row_s + 16u * (uint32_t)i));
+                            const uint32_t y0 = 4u * (uint32_t)__float_as_int(ri.x), y1 = 4u * (uint32_t)__float_as_int(ri.y);
+                            float v00, v01, v10, v11;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v00) : "r"(a0 + y0));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v01) : "r"(a1 + y0));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v10) : "r"(a0 + y1));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v11) : "r"(a1 + y1));
+                            if (!BWD) {
+                                float a = __fmul_rn(v00, __fmul_rn(cj.z, ri.z));
+                                a = fmaf(v01, __fmul_rn(cj.w, ri.z), a);
+                                a = fmaf(v10, __fmul_rn(cj.z, ri.w), a);
+                                a = fmaf(v11, __fmul_rn(cj.w, ri.w), a);
+                                *op = a;
+                                op += step;
+                            } else {
+                                // grid_sampler_2d_backward: d out / d ix, d out / d iy; zero where the coordinate was clamped
+                                const float dgx = g[u] * ((v01 - v00) * ri.z + (v11 - v10) * ri.w) * col_m;
+                                const float dgy = g[u] * ((v10 - v00) * cj.z + (v11 - v01) * cj.w) * row_m[i];
+                                acc[0] += dgx;
+                                acc[1] += dgy;
+                                acc[2] = fmaf(dgx, bx, acc[2]);
+                                acc[3] = fmaf(dgy, base_y[i], acc[3]);
+                            }
                         }
                     }
                 }
