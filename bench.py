@@ -594,6 +594,24 @@ def run_ours(args):
             blk = secondary_workload("D", 256, "weak", rank, world, dev, local_rank, max(3, min(args.steps, 5)), 3)
             if line is not None:
                 line["config_D"] = blk
+        # the opt-in tensor-core sweep (SPAIR_SWEEP_TC=1, csrc/sweep_tc.cuh) on the same two workloads.  NOT the headline:
+        # its split-precision TF32 layers are ~1e-6 accurate instead of ~1e-7 and this model's backward amplifies that beyond
+        # rtol 1e-4 on one golden case, so `value` above stays on the fp32 SIMT sweep.
+        os.environ["SPAIR_SWEEP_TC"] = "1"
+        try:
+            tc = {}
+            for key, (cfg_name, gb, scal) in (("configs[1]", (args.config, B, "weak")), ("strong_scaling_C", ("C", 512, "strong"))):
+                blk = secondary_workload(cfg_name, gb, scal, rank, world, dev, local_rank, args.steps, args.warmup)
+                blk["kernels"] = {k: v for k, v in blk.get("kernels", {}).items() if k.startswith("sweep")}
+                blk.pop("limiting_kernel", None)
+                tc[key] = blk
+            if line is not None:
+                tc["note"] = ("same workloads with SPAIR_SWEEP_TC=1: the dense layers of the two sweep kernels on tcgen05 (TF32 hi/lo "
+                              "split, weights as the M-side operand, bulk-copy weight stream); reported beside the headline, which "
+                              "uses the fp32 SIMT sweep (parity-exact)")
+                line["tc_sweep"] = tc
+        finally:
+            del os.environ["SPAIR_SWEEP_TC"]
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.config)

@@ -26,7 +26,7 @@ extern "C" {
 
 #define SPAIR_ERR_INVALID (-1)
 #define SPAIR_MAX_NEIGHBOURS 12
-#define SPAIR_ABI_VERSION 3   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows; 3: tcgen05 GEMM */
+#define SPAIR_ABI_VERSION 4   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows; 3: tcgen05 GEMM; 4: tcgen05 sweep */
 
 int spair_abi_version(void);
 
@@ -328,6 +328,44 @@ int spair_sweep_bwd(const spair_sweep_dims* dims, const int* order, const int* s
                     const float* d_zw, const float* d_attr, const float* d_depth, const float* d_pres,
                     const float* d_dmean, const float* d_dstd,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * The same two sweeps with their dense layers (reference modules.py:124-165, called inside the loop of
+ * models.py:68-117) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 in split precision
+ * (x = hi + lo; W_hi*[x_hi | x_lo] as one N = 32 MMA + W_lo*x_hi as one N = 16 MMA per k-step, fp32
+ * accumulation in TMEM), weights as the M-side operand so an MMA costs what the <= 16 activation rows of a
+ * CTA cost.  spair_sweep_tc_pack splits and swizzles all 12 weight matrices once per step into the exact
+ * shared-memory image of the operand tiles, in consumption order, one stream per direction
+ * (spair_sweep_tc_stream_floats floats each); the kernels stream them with bulk async copies through an
+ * mbarrier ring that runs ahead across layer boundaries.  Arguments, buffers, limits and results are those
+ * of spair_sweep_fwd / spair_sweep_bwd (results agree to ~1e-6 relative: different summation order).  The `wt`
+ * fields of spair_sweep_mlp hold the UNPACKED nn.Linear weights [n][k] here: a hidden unit whose pre-activation is
+ * within the split-precision rounding error of zero is re-evaluated from the fp32 operands with float64
+ * accumulation, so the ReLU branch (and with it every gradient through the unit) is the exact one.  The `w`
+ * fields of spair_sweep_mlp_bwd are ignored.  n / k: 12 layers in the order box0, box1, box2,
+ * enc0 .. obj2 (nn.Linear weight [n][k]).
+ * ---------------------------------------------------------------------------------- */
+int spair_sweep_tc_stream_floats(const int* n, const int* k, int n_layers /* 12 */, int backward);
+int spair_sweep_tc_pack(const float* const* w /* host array of 12 device pointers */, const int* n, const int* k,
+                        int n_layers, float* fwd_stream, float* bwd_stream /* either may be NULL */, void* stream);
+int spair_sweep_fwd_tc(const spair_sweep_dims* dims, const int* order, const int* starts, const int* nb_offsets,
+                       const float* image, const float* feat, const float* edge,
+                       const float* eps_where, const float* eps_attr, const float* eps_depth, const float* u_pres,
+                       const spair_box_geom* geom,
+                       const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                       const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp,
+                       float* box, float* z_where, float* attr, float* depth, float* pres,
+                       float* dmean, float* dstd,
+                       const float* fwd_stream, void* stream);
+int spair_sweep_bwd_tc(const spair_sweep_dims* dims, const int* order, const int* starts, const int* wf_pos,
+                       const int* nb_offsets, const float* image, const float* z_where,
+                       const float* eps_where, const float* eps_attr, const float* eps_depth, const float* u_pres,
+                       const float* wheel, const spair_box_geom* geom,
+                       const spair_sweep_mlp_bwd* box_mlp, const spair_sweep_mlp_bwd* enc_mlp,
+                       const spair_sweep_mlp_bwd* z_mlp, const spair_sweep_mlp_bwd* obj_mlp,
+                       const float* d_zw, const float* d_attr, const float* d_depth, const float* d_pres,
+                       const float* d_dmean, const float* d_dstd,
+                       const float* bwd_stream, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Backbone stem (caller side of the path): nn.ZeroPad2d + the first Conv2d + bias + ReLU of

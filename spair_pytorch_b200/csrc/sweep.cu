@@ -12,6 +12,8 @@
 // wavefront-major global buffers the unfused path uses, so the backward pass (and the weight-gradient GEMMs) are
 // unchanged.  This replaces ~27 launches per wavefront (12 cuBLAS GEMMs of <= 1536 rows, 8 elementwise, 6 head
 // kernels) whose issue-to-issue latency, not their arithmetic, bounded the step.
+#include <stdlib.h>
+
 #include "warp_math.cuh"
 
 namespace spair {
@@ -33,8 +35,21 @@ __device__ long long g_sw_timing[64];
 #define SW_MARK(i)
 #endif
 
+}  // namespace spair
+#include "sweep_tc.cuh"
+namespace spair {
+
+// block barrier of the sweep's 512 threads: the whole CTA in the SIMT kernels, named barrier 1 in the tensor-core kernels
+// (their producer / MMA-issuer warps never join it)
+template <bool TC>
+__device__ __forceinline__ void sw_sync() {
+    if (TC) tc::workers_sync();
+    else __syncthreads();
+}
+
 struct SweepLayer {
-    const float4* Wp;  // [ceil(K/4)][N] packed weight: Wp[g][n] = W[n][4g .. 4g+3], zero padded
+    const float4* Wp;  // [ceil(K/4)][N] packed weight: Wp[g][n] = W[n][4g .. 4g+3], zero padded (tensor-core sweep: the
+                       // UNPACKED nn.Linear weight [N][K], read only to re-evaluate ReLU pre-activations near zero)
     const float* b;    // [N]
     int K, N;
 };
@@ -265,16 +280,54 @@ __device__ __forceinline__ void mlp3(const SweepMLP& M, const int* grow, int nro
     SW_MARK(12);
 }
 
+// the same MLP on the tensor cores: the input rows go from global memory straight into operand tiles, the hidden
+// activations from the epilogue registers into the next layer's operand tiles (sweep_tc.cuh)
+__device__ __forceinline__ void mlp3_tc(tc::Worker& W, const SweepMLP& M, const int* grow, int nrows, float* y) {
+    SW_T0();
+    tc::workers_sync();                                 // the input rows written by other threads are visible
+    const int row = threadIdx.x >> 5;
+    tc::stage_rows(W, M.X + (size_t)grow[row] * M.ldX, row < nrows, M.l[0].K);
+    SW_MARK(10);
+    const tc::Kink k0{reinterpret_cast<const float*>(M.l[0].Wp), M.X, M.ldX};
+    const tc::Kink k1{reinterpret_cast<const float*>(M.l[1].Wp), M.H0, M.l[0].N};
+    const tc::Kink none{nullptr, nullptr, 0};
+    tc::epilogue(W, M.l[0].K, M.l[0].N, M.l[0].b, true, nullptr, grow, nrows, M.H0, M.l[0].N, true, nullptr, 0, k0, 20);
+    SW_MARK(11);
+    tc::epilogue(W, M.l[1].K, M.l[1].N, M.l[1].b, true, nullptr, grow, nrows, M.H1, M.l[1].N, true, nullptr, 0, k1, 20);
+    SW_MARK(13);
+    tc::epilogue(W, M.l[2].K, M.l[2].N, M.l[2].b, false, nullptr, grow, nrows, M.Y, M.l[2].N, false, y, kSwHP, none, 20);
+    tc::workers_sync();
+    SW_MARK(12);
+}
+
 __device__ __forceinline__ int sw_box_slot(int k) { return k == 0 ? 1 : (k == 1 ? 0 : (k == 2 ? 3 : 2)); }
 
-__global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p) {
+// TC = false: SIMT dense layers (512 threads).  TC = true: tensor-core dense layers (sweep_tc.cuh; 576 threads: the same
+// 16 worker warps + a bulk-copy producer warp + an MMA-issuer warp); everything between the MLPs is the same code.
+template <bool TC>
+__global__ void __launch_bounds__(TC ? tc::kThreads : kSwThreads, 1)
+sweep_fwd_kernel(const SweepFwdArgs p, const tc::Plan plan, const float* __restrict__ wstream, int stages_per_wavefront) {
     static_assert(kSwThreads / 32 == kSwRows, "one warp stages one input row");
+    static_assert(kSwThreads == tc::kWorkers && kSwRows == tc::kRows, "worker layout of the tensor-core path");
     extern __shared__ __align__(16) float sm[];
-    float* chunk = sm;                                  // [kSwRows][kSwKCP]
-    float* part = chunk + kSwRows * kSwKCP;             // [kSwPart] split-K partial sums
-    float* ha = part + kSwPart;                         // [kSwRows][kSwHP]
-    float* hb = ha + kSwRows * kSwHP;
-    float* y = hb + kSwRows * kSwHP;
+    float *chunk = nullptr, *part = nullptr, *ha = nullptr, *hb = nullptr, *y;
+    tc::Worker W;
+    uint32_t wring = 0;
+    if (TC) {
+        // [weight ring | activation ring] (1024-byte aligned for the 128-byte swizzle) | barriers | row-major buffers
+        const uint32_t raw = tc::smem_u32(sm), base = (raw + 1023u) & ~1023u;
+        wring = base;
+        W.xring = base + tc::kWStages * tc::kStageBytes;
+        W.b.base = base + tc::kRingBytes;
+        W.x_prod = 0; W.acc_cnt = 0;
+        y = reinterpret_cast<float*>(reinterpret_cast<char*>(sm) + (base - raw) + tc::kRingBytes + tc::kBarBytes);
+    } else {
+        chunk = sm;                                     // [kSwRows][kSwKCP]
+        part = chunk + kSwRows * kSwKCP;                // [kSwPart] split-K partial sums
+        ha = part + kSwPart;                            // [kSwRows][kSwHP]
+        hb = ha + kSwRows * kSwHP;
+        y = hb + kSwRows * kSwHP;
+    }
     float* base_g = y + kSwRows * kSwHP;                // [kSwMaxG] normalised base grid of the glimpse
     float* zw_s = base_g + kSwMaxG;                     // [kSwRows][4] boxes of the current rows
     int* grow = reinterpret_cast<int*>(zw_s + kSwRows * 4);   // [kSwRows] global row of each local row
@@ -284,6 +337,34 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
     const int b0 = blockIdx.x * p.ipc;
     const int n_img = min(p.ipc, p.B - b0);
     if (n_img <= 0) return;
+    if (TC) {
+        const int warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) tc::init_barriers(W.b);
+        if (warp == tc::kMmaWarp) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(W.b.tmem_slot()), "n"(tc::kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        tc::fence_before();
+        __syncthreads();
+        tc::fence_after();
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(W.tmem) : "r"(W.b.tmem_slot()));
+        if (warp >= tc::kProducerWarp) {
+            if (threadIdx.x == tc::kProducerWarp * 32) tc::producer_loop(wring, W.b, wstream, stages_per_wavefront, p.n_wavefronts);
+            // (an exact thread index: the compiler then keeps the descriptors in uniform registers; with a per-warp lane test
+            // it wraps every tcgen05.mma in a broadcast loop and the issue rate drops by a third)
+            if (threadIdx.x == tc::kMmaWarp * 32) tc::mma_loop<0>(wring, W.xring, W.b, W.tmem, plan, p.n_wavefronts);
+            if (threadIdx.x == (tc::kMmaWarp + 1) * 32) tc::mma_loop<1>(wring, W.xring, W.b, W.tmem, plan, p.n_wavefronts);
+            __syncwarp();
+            tc::fence_before();
+            __syncthreads();                            // the workers are done: every MMA has been consumed
+            if (warp == tc::kMmaWarp) {
+                __syncwarp();
+                tc::fence_after();
+                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(W.tmem), "n"(tc::kTmemCols));
+            }
+            return;
+        }
+    }
     const int E = p.A + 6, D = 4 + p.A + 1;
     const int CTX = p.nb.n * E;
     const int c_pt = p.F + CTX, c_box = c_pt + p.P, c_attr = c_box + 4, c_depth = c_attr + p.A;
@@ -294,7 +375,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
     for (int t = 0; t < p.n_wavefronts; ++t) {
         const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
         const int nrows = n_cells * n_img;
-        __syncthreads();                                // previous wavefront's latents are visible; row tables free
+        sw_sync<TC>();                                // previous wavefront's latents are visible; row tables free
         if (threadIdx.x < kSwRows) {
             const int r = threadIdx.x;
             if (r < nrows) {
@@ -306,7 +387,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
                 grow[r] = 0; rcell[r] = 0; rimg[r] = b0;
             }
         }
-        __syncthreads();
+        sw_sync<TC>();
 
         // ---- L0: lateral context -> input columns [0, F+CTX) of the three networks (models.py:73,76) ----
         const int width = p.F + CTX;
@@ -340,7 +421,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
         SW_MARK(0);
 
         // ---- z_where: box network + box head (models.py:76-79, 322-381) ----
-        mlp3(p.box, grow, nrows, chunk, part, ha, hb, y);
+        if (TC) mlp3_tc(W, p.box, grow, nrows, y);
+        else mlp3(p.box, grow, nrows, chunk, part, ha, hb, y);
         SW_MARK(1);
         for (int idx = threadIdx.x; idx < nrows * (4 + p.P); idx += kSwThreads) {
             const int r = idx / (4 + p.P), k = idx - r * (4 + p.P);
@@ -374,7 +456,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
             p.z.X[g * p.z.ldX + c_box + slot] = bval;
             p.obj.X[g * p.obj.ldX + c_box + slot] = bval;
         }
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(2);
 
         // ---- z_what: glimpse (modules.py:216-273, border padding) -> encoder input rows ----
@@ -403,7 +485,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
             }
         }
         SW_MARK(3);
-        mlp3(p.enc, grow, nrows, chunk, part, ha, hb, y);
+        if (TC) mlp3_tc(W, p.enc, grow, nrows, y);
+        else mlp3(p.enc, grow, nrows, chunk, part, ha, hb, y);
         SW_MARK(4);
         for (int idx = threadIdx.x; idx < nrows * p.A; idx += kSwThreads) {
             const int r = idx / p.A, k = idx - r * p.A;
@@ -422,7 +505,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
 
         // ---- z_depth (models.py:88-97) ----
         SW_MARK(5);
-        mlp3(p.z, grow, nrows, chunk, part, ha, hb, y);
+        if (TC) mlp3_tc(W, p.z, grow, nrows, y);
+        else mlp3(p.z, grow, nrows, chunk, part, ha, hb, y);
         SW_MARK(6);
         for (int idx = threadIdx.x; idx < nrows * (1 + p.P); idx += kSwThreads) {
             const int r = idx / (1 + p.P), k = idx - r * (1 + p.P);
@@ -444,7 +528,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
 
         // ---- z_pres (models.py:100-105, 393-411) ----
         SW_MARK(7);
-        mlp3(p.obj, grow, nrows, chunk, part, ha, hb, y);
+        if (TC) mlp3_tc(W, p.obj, grow, nrows, y);
+        else mlp3(p.obj, grow, nrows, chunk, part, ha, hb, y);
         SW_MARK(8);
         if (threadIdx.x < nrows) {
             const int r = threadIdx.x;
@@ -453,6 +538,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_fwd_kernel(SweepFwdArgs p
             const float noise = logf(u + 10e-10f) - logf(1.0f - u + 10e-10f);
             p.pres[o] = sigmoid_f(clamp10(y[r * kSwHP]) + noise);
         }
+    }
+    if (TC) {
+        tc::fence_before();
+        __syncthreads();                                // pairs with the producer / MMA warps' closing barrier
     }
 }
 
@@ -542,14 +631,45 @@ __device__ __forceinline__ void mlp3_bwd(const SweepMLPBwd& M, const int* grow, 
     dense_bwd_layer(M.W[0], M.N[0], M.K[0], gb, nullptr, grow, nrows, part, nullptr, M.dX, M.ldX);
 }
 
-__global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p) {
+// the same chain on the tensor cores (sweep_tc.cuh): gy (row-major, written by the head phase) -> operand tiles -> dH1 -> dH0 -> dX
+__device__ __forceinline__ void mlp3_bwd_tc(tc::Worker& W, const SweepMLPBwd& M, const int* grow, int nrows, const float* gy) {
+    SW_T0();
+    const int row = threadIdx.x >> 5;
+    tc::stage_rows(W, gy + row * kSwHP, row < nrows, M.N[2]);
+    SW_MARK(43);
+    const tc::Kink none{nullptr, nullptr, 0};
+    tc::epilogue(W, M.N[2], M.K[2], nullptr, false, M.H1, grow, nrows, M.dH1, M.K[2], true, nullptr, 0, none, 40);
+    SW_MARK(44);
+    tc::epilogue(W, M.N[1], M.K[1], nullptr, false, M.H0, grow, nrows, M.dH0, M.K[1], true, nullptr, 0, none, 40);
+    SW_MARK(45);
+    tc::epilogue(W, M.N[0], M.K[0], nullptr, false, nullptr, grow, nrows, M.dX, M.ldX, false, nullptr, 0, none, 40);
+    tc::workers_sync();                                 // dX rows are read back from global memory by the head phases
+    SW_MARK(46);
+}
+
+template <bool TC>
+__global__ void __launch_bounds__(TC ? tc::kThreads : kSwThreads, 1)
+sweep_bwd_kernel(const SweepBwdArgs p, const tc::Plan plan, const float* __restrict__ wstream, int stages_per_wavefront) {
     static_assert(kSwThreads / 32 == kSwRows, "the glimpse gradient uses one warp per row");
     extern __shared__ __align__(16) float sm[];
-    float* part = sm;                                   // [kSwPart] split-K partial sums
-    float* gy = part + kSwPart;                         // [kSwRows][kSwHP] dY of the current network
-    float* ga = gy + kSwRows * kSwHP;
-    float* gb = ga + kSwRows * kSwHP;
-    float* dcell = gb + kSwRows * kSwHP;                // [kSwRows][64] gradient through the lateral context
+    float *part = nullptr, *gy, *ga = nullptr, *gb = nullptr, *dcell;
+    tc::Worker W;
+    uint32_t wring = 0;
+    if (TC) {
+        const uint32_t raw = tc::smem_u32(sm), base = (raw + 1023u) & ~1023u;
+        wring = base;
+        W.xring = base + tc::kWStages * tc::kStageBytes;
+        W.b.base = base + tc::kRingBytes;
+        W.x_prod = 0; W.acc_cnt = 0;
+        gy = reinterpret_cast<float*>(reinterpret_cast<char*>(sm) + (base - raw) + tc::kRingBytes + tc::kBarBytes);
+        dcell = gy + kSwRows * kSwHP;
+    } else {
+        part = sm;                                      // [kSwPart] split-K partial sums
+        gy = part + kSwPart;                            // [kSwRows][kSwHP] dY of the current network
+        ga = gy + kSwRows * kSwHP;
+        gb = ga + kSwRows * kSwHP;
+        dcell = gb + kSwRows * kSwHP;                   // [kSwRows][64] gradient through the lateral context
+    }
     float* base_g = dcell + kSwRows * 64;               // [kSwMaxG]
     float* dzw = base_g + kSwMaxG;                      // [kSwRows][4] glimpse gradient wrt z_where
     int* grow = reinterpret_cast<int*>(dzw + kSwRows * 4);
@@ -559,6 +679,34 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
     const int b0 = blockIdx.x * p.ipc;
     const int n_img = min(p.ipc, p.B - b0);
     if (n_img <= 0) return;
+    if (TC) {
+        const int warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) tc::init_barriers(W.b);
+        if (warp == tc::kMmaWarp) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(W.b.tmem_slot()), "n"(tc::kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        tc::fence_before();
+        __syncthreads();
+        tc::fence_after();
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(W.tmem) : "r"(W.b.tmem_slot()));
+        if (warp >= tc::kProducerWarp) {
+            if (threadIdx.x == tc::kProducerWarp * 32) tc::producer_loop(wring, W.b, wstream, stages_per_wavefront, p.n_wavefronts);
+            // (an exact thread index: the compiler then keeps the descriptors in uniform registers; with a per-warp lane test
+            // it wraps every tcgen05.mma in a broadcast loop and the issue rate drops by a third)
+            if (threadIdx.x == tc::kMmaWarp * 32) tc::mma_loop<0>(wring, W.xring, W.b, W.tmem, plan, p.n_wavefronts);
+            if (threadIdx.x == (tc::kMmaWarp + 1) * 32) tc::mma_loop<1>(wring, W.xring, W.b, W.tmem, plan, p.n_wavefronts);
+            __syncwarp();
+            tc::fence_before();
+            __syncthreads();
+            if (warp == tc::kMmaWarp) {
+                __syncwarp();
+                tc::fence_after();
+                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(W.tmem), "n"(tc::kTmemCols));
+            }
+            return;
+        }
+    }
     const int E = p.A + 6, D = 4 + p.A + 1;
     const int CTX = p.nb.n * E;
     const int c_pt = p.F + CTX, c_box = c_pt + p.P, c_attr = c_box + 4, c_depth = c_attr + p.A;
@@ -570,7 +718,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
     for (int t = p.n_wavefronts - 1; t >= 0; --t) {
         const int s0 = p.starts[t], n_cells = p.starts[t + 1] - s0;
         const int nrows = n_cells * n_img;
-        __syncthreads();
+        sw_sync<TC>();
         if (threadIdx.x < kSwRows) {
             const int r = threadIdx.x;
             if (r < nrows) {
@@ -582,7 +730,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
                 grow[r] = 0; rcell[r] = 0; rimg[r] = b0;
             }
         }
-        __syncthreads();
+        sw_sync<TC>();
 
         // ---- gradient arriving through the lateral context of later cells (models.py:106 -> 73) ----
         for (int idx = threadIdx.x; idx < nrows * E; idx += kSwThreads) {
@@ -599,7 +747,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             }
             dcell[r * 64 + j] = acc;
         }
-        __syncthreads();
+        sw_sync<TC>();
 
         // ---- z_pres (models.py:393-411) ----
         if (threadIdx.x < kSwRows) {
@@ -617,9 +765,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + 0] = dy;
             gy[r * kSwHP + 1] = gy[r * kSwHP + 2] = gy[r * kSwHP + 3] = 0.0f;
         }
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(30);
-        mlp3_bwd(p.obj, grow, nrows, part, gy, ga, gb);
+        if (TC) mlp3_bwd_tc(W, p.obj, grow, nrows, gy);
+        else mlp3_bwd(p.obj, grow, nrows, part, gy, ga, gb);
         SW_MARK(31);
 
         // ---- z_depth (models.py:88-97) ----
@@ -646,9 +795,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + k] = v;
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 + p.P + (idx & 3)] = 0.0f;
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(32);
-        mlp3_bwd(p.z, grow, nrows, part, gy, ga, gb);
+        if (TC) mlp3_bwd_tc(W, p.z, grow, nrows, gy);
+        else mlp3_bwd(p.z, grow, nrows, part, gy, ga, gb);
         SW_MARK(33);
 
         // ---- z_what (models.py:83-85) ----
@@ -671,9 +821,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + p.A + k] = vs;
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 2 * p.A + (idx & 3)] = 0.0f;
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(34);
-        mlp3_bwd(p.enc, grow, nrows, part, gy, ga, gb);
+        if (TC) mlp3_bwd_tc(W, p.enc, grow, nrows, gy);
+        else mlp3_bwd(p.enc, grow, nrows, part, gy, ga, gb);
         SW_MARK(35);
 
         // ---- glimpse: d z_where (modules.py:216-273; the image has no gradient in the model) ----
@@ -719,7 +870,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
             if (lane == 0) { dzw[r * 4 + 0] = a0; dzw[r * 4 + 1] = a1; dzw[r * 4 + 2] = a2; dzw[r * 4 + 3] = a3; }
         }
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(38);
 
         // ---- z_where: box head (models.py:322-381) ----
@@ -761,10 +912,15 @@ __global__ void __launch_bounds__(kSwThreads, 1) sweep_bwd_kernel(SweepBwdArgs p
             gy[r * kSwHP + k] = v;
         }
         for (int idx = threadIdx.x; idx < kSwRows * 4; idx += kSwThreads) gy[(idx >> 2) * kSwHP + 8 + p.P + (idx & 3)] = 0.0f;
-        __syncthreads();
+        sw_sync<TC>();
         SW_MARK(36);
-        mlp3_bwd(p.box, grow, nrows, part, gy, ga, gb);
+        if (TC) mlp3_bwd_tc(W, p.box, grow, nrows, gy);
+        else mlp3_bwd(p.box, grow, nrows, part, gy, ga, gb);
         SW_MARK(37);
+    }
+    if (TC) {
+        tc::fence_before();
+        __syncthreads();                                // pairs with the producer / MMA warps' closing barrier
     }
 }
 
@@ -798,9 +954,93 @@ __global__ void __launch_bounds__(256) sweep_pack_kernel(PackArgs p) {
     }
 }
 
+// ---- weight stream of the tensor-core sweeps --------------------------------------------------------------------------
+// One CTA per stage (= 128 output features x 32 reduction indices, hi tile then lo tile, each in the 128-byte-swizzled
+// K-major operand layout), stages in the order tc::mma_loop consumes them: layers in execution order; inside a layer
+// chunk (256 reduction indices) -> feature tile -> k-block.  backward stream: execution order obj, z, enc, box, layers
+// 2, 1, 0, operand = W^T (features = the layer's inputs, reduction over its outputs).
+struct TcPackArgs {
+    const float* W[tc::kMaxLayers];
+    int N[tc::kMaxLayers], K[tc::kMaxLayers];    // nn.Linear weight [N][K], model order box0..box2, enc0.., z0.., obj0..
+    float* fwd; float* bwd;
+    int stages_fwd;
+};
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackArgs a) {
+    int s = blockIdx.x;
+    const bool bwd = s >= a.stages_fwd;
+    if (bwd) s -= a.stages_fwd;
+    float* dst = (bwd ? a.bwd : a.fwd) + (size_t)s * tc::kStageFloats;
+    if (dst == nullptr || (bwd ? a.bwd : a.fwd) == nullptr) return;
+    int l = 0, Kred = 0, Mout = 0;
+    for (int e = 0; e < tc::kMaxLayers; ++e) {
+        l = bwd ? 3 * (3 - e / 3) + (2 - e % 3) : e;
+        Kred = bwd ? a.N[l] : a.K[l];
+        Mout = bwd ? a.K[l] : a.N[l];
+        const int cnt = tc::stages_of(Kred, Mout);
+        if (s < cnt) break;
+        s -= cnt;
+    }
+    const int KB = (Kred + 31) >> 5, tiles = (Mout + 127) >> 7, chunks = (Kred + tc::kChunkK - 1) / tc::kChunkK;
+    int mt = 0, kb = 0;
+    for (int g0 = 0, rem = s, found = 0; g0 < tiles && !found; g0 += tc::kTileGroup) {      // the loops of tc::mma_loop
+        const int gt = min(tc::kTileGroup, tiles - g0);
+        for (int c = 0; c < chunks; ++c) {
+            const int kbn = min(tc::kChunkKB, KB - tc::kChunkKB * c);
+            if (rem < gt * kbn) {
+                mt = g0 + rem / kbn;
+                kb = tc::kChunkKB * c + rem % kbn;
+                found = 1;
+                break;
+            }
+            rem -= gt * kbn;
+        }
+    }
+    const float* __restrict__ W = a.W[l];
+    const int ldw = a.K[l];
+    for (int i = threadIdx.x; i < 128 * 32; i += 256) {
+        const int fl = bwd ? (i & 127) : (i >> 5), kl = bwd ? (i >> 7) : (i & 31);     // coalesced along W's contiguous index
+        const int f = mt * 128 + fl, k = kb * 32 + kl;
+        float v = 0.0f;
+        if (f < Mout && k < Kred) v = bwd ? __ldg(W + (size_t)k * ldw + f) : __ldg(W + (size_t)f * ldw + k);
+        uint32_t hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const int o = fl * 32 + ((((kl >> 2) ^ fl) & 7) << 2) + (kl & 3);
+        dst[o] = __uint_as_float(hi);
+        dst[o + 4096] = __uint_as_float(lo);
+    }
+}
+
 }  // namespace spair
 
 using namespace spair;
+
+static int tc_stages(const int* n, const int* k, int backward) {
+    int total = 0;
+    for (int l = 0; l < tc::kMaxLayers; ++l) total += backward ? tc::stages_of(n[l], k[l]) : tc::stages_of(k[l], n[l]);
+    return total;
+}
+
+extern "C" int spair_sweep_tc_stream_floats(const int* n, const int* k, int n_layers, int backward) {
+    if (!n || !k || n_layers != tc::kMaxLayers) return -1;
+    return tc_stages(n, k, backward) * tc::kStageFloats;
+}
+
+extern "C" int spair_sweep_tc_pack(const float* const* w, const int* n, const int* k, int n_layers, float* fwd_stream,
+                                   float* bwd_stream, void* stream) {
+    SPAIR_REQUIRE(w && n && k && n_layers == tc::kMaxLayers && (fwd_stream || bwd_stream));
+    SPAIR_REQUIRE(((uintptr_t)fwd_stream % 16) == 0 && ((uintptr_t)bwd_stream % 16) == 0);
+    TcPackArgs a;
+    for (int l = 0; l < tc::kMaxLayers; ++l) {
+        SPAIR_REQUIRE(w[l] && n[l] > 0 && k[l] > 0);
+        a.W[l] = w[l]; a.N[l] = n[l]; a.K[l] = k[l];
+    }
+    a.fwd = fwd_stream; a.bwd = bwd_stream;
+    a.stages_fwd = tc_stages(n, k, 0);
+    const int total = a.stages_fwd + tc_stages(n, k, 1);
+    tc_pack_kernel<<<total, 256, 0, (cudaStream_t)stream>>>(a);
+    SPAIR_LAUNCH_CHECK();
+}
 
 extern "C" int spair_sweep_pack_weights(const spair_sweep_pack* layers, int n_layers, void* stream) {
     SPAIR_REQUIRE(layers && n_layers >= 1 && n_layers <= kPackMaxLayers);
@@ -820,11 +1060,11 @@ extern "C" int spair_sweep_pack_weights(const spair_sweep_pack* layers, int n_la
 }
 
 // Host-side description of one MLP for spair_sweep_fwd (mirrors the C struct in include/spair_b200.h)
-static bool to_mlp(const spair_sweep_mlp* m, SweepMLP& out) {
+static bool to_mlp(const spair_sweep_mlp* m, SweepMLP& out, bool packed_w) {
     if (!m || !m->x || !m->h0 || !m->h1 || !m->y) return false;
     for (int i = 0; i < 3; ++i) {
         if (!m->wt[i] || !m->b[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
-        if ((uintptr_t)m->wt[i] % 16) return false;
+        if (packed_w && (uintptr_t)m->wt[i] % 16) return false;
         out.l[i] = SweepLayer{reinterpret_cast<const float4*>(m->wt[i]), m->b[i], m->k[i], m->n[i]};
     }
     if (m->k[1] != m->n[0] || m->k[2] != m->n[1] || m->ld_x < m->k[0]) return false;
@@ -845,12 +1085,13 @@ extern "C" int spair_debug_sweep_timing(long long* out64) {
 }
 #endif
 
-extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
-                               const float* image, const float* feat, const float* edge, const float* eps_where,
-                               const float* eps_attr, const float* eps_depth, const float* u_pres,
-                               const spair_box_geom* geom, const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
-                               const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp, float* box, float* z_where,
-                               float* attr, float* depth, float* pres, float* dmean, float* dstd, void* stream) {
+static int sweep_fwd_impl(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
+                          const float* image, const float* feat, const float* edge, const float* eps_where,
+                          const float* eps_attr, const float* eps_depth, const float* u_pres,
+                          const spair_box_geom* geom, const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                          const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp, float* box, float* z_where,
+                          float* attr, float* depth, float* pres, float* dmean, float* dstd, const float* wstream, bool use_tc,
+                          void* stream) {
     SPAIR_REQUIRE(d && order && starts && nb_offsets && image && feat && edge && eps_where && eps_attr && eps_depth && u_pres);
     SPAIR_REQUIRE(geom && box && z_where && attr && depth && pres && dmean && dstd);
     SPAIR_REQUIRE(d->B > 0 && d->HW == d->Hc * d->Wc && d->G > 0 && d->G <= kSwMaxG && d->ipc >= 1 && d->n_wavefronts > 0);
@@ -862,26 +1103,78 @@ extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, cons
     for (int i = 0; i < d->n_nb; ++i) { a.nb.dh[i] = nb_offsets[2 * i]; a.nb.dw[i] = nb_offsets[2 * i + 1]; }
     a.order = order; a.starts = starts; a.image = image; a.feat = feat; a.edge = edge;
     a.eps_where = eps_where; a.eps_attr = eps_attr; a.eps_depth = eps_depth; a.u_pres = u_pres; a.geom = *geom;
-    SPAIR_REQUIRE(to_mlp(box_mlp, a.box) && to_mlp(enc_mlp, a.enc) && to_mlp(z_mlp, a.z) && to_mlp(obj_mlp, a.obj));
+    SPAIR_REQUIRE(to_mlp(box_mlp, a.box, !use_tc) && to_mlp(enc_mlp, a.enc, !use_tc) && to_mlp(z_mlp, a.z, !use_tc) &&
+                  to_mlp(obj_mlp, a.obj, !use_tc));
     const int E = d->A + 6, CTX = d->n_nb * E;
     SPAIR_REQUIRE(a.box.l[0].K == d->F + CTX && a.box.l[2].N == 8 + d->P);
     SPAIR_REQUIRE(a.enc.l[0].K == d->C * d->G * d->G && a.enc.l[2].N == 2 * d->A);
     SPAIR_REQUIRE(a.z.l[0].K == d->F + CTX + d->P + 4 + d->A && a.z.l[2].N == 2 + d->P);
     SPAIR_REQUIRE(a.obj.l[0].K == a.z.l[0].K + 1 && a.obj.l[2].N == 1);
     a.out_box = box; a.z_where = z_where; a.attr = attr; a.depth = depth; a.pres = pres; a.dmean = dmean; a.dstd = dstd;
+    const int grid = (d->B + d->ipc - 1) / d->ipc;
+    tc::Plan plan;
+    plan.n_layers = 0;
+    if (use_tc) {
+        SPAIR_REQUIRE(wstream && ((uintptr_t)wstream % 16) == 0);
+        if (getenv("SPAIR_SWEEP_TC_NO_RELU_FIXUP")) {      // diagnostic: what the exact-ReLU re-evaluation costs
+            SweepMLP* mm[4] = {&a.box, &a.enc, &a.z, &a.obj};
+            for (int m = 0; m < 4; ++m)
+                for (int i = 0; i < 3; ++i) mm[m]->l[i].Wp = nullptr;
+        }
+        const SweepMLP* ms[4] = {&a.box, &a.enc, &a.z, &a.obj};
+        int stages = 0;
+        for (int m = 0; m < 4; ++m)
+            for (int i = 0; i < 3; ++i) {
+                plan.K[plan.n_layers] = ms[m]->l[i].K; plan.M[plan.n_layers] = ms[m]->l[i].N;
+                stages += tc::stages_of(ms[m]->l[i].K, ms[m]->l[i].N);
+                ++plan.n_layers;
+            }
+        const size_t smem = 1024 + tc::kRingBytes + tc::kBarBytes + sizeof(float) * (size_t)(kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
+                            sizeof(int) * 3 * kSwRows;
+        static size_t smem_set_tc[kMaxDevices] = {0};
+        if (ensure_dynamic_smem(sweep_fwd_kernel<true>, smem, smem_set_tc) != cudaSuccess) return (int)cudaGetLastError();
+        sweep_fwd_kernel<true><<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(a, plan, wstream, stages);
+        SPAIR_LAUNCH_CHECK();
+    }
     const size_t smem = sizeof(float) * (size_t)(kSwRows * kSwKCP + kSwPart + 3 * kSwRows * kSwHP + kSwMaxG + kSwRows * 4) +
                         sizeof(int) * 3 * kSwRows;
     static size_t smem_set[kMaxDevices] = {0};
-    if (ensure_dynamic_smem(sweep_fwd_kernel, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
-    const int grid = (d->B + d->ipc - 1) / d->ipc;
-    sweep_fwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
+    if (ensure_dynamic_smem(sweep_fwd_kernel<false>, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
+    sweep_fwd_kernel<false><<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a, plan, nullptr, 0);
     SPAIR_LAUNCH_CHECK();
 }
 
-static bool to_mlp_bwd(const spair_sweep_mlp_bwd* m, SweepMLPBwd& out) {
+#ifdef SW_TIMING
+extern "C" int spair_debug_sweep_tc_flags(int flags) {
+    return (int)cudaMemcpyToSymbol(tc::g_tc_debug, &flags, sizeof(int));
+}
+#endif
+
+extern "C" int spair_sweep_fwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
+                               const float* image, const float* feat, const float* edge, const float* eps_where,
+                               const float* eps_attr, const float* eps_depth, const float* u_pres,
+                               const spair_box_geom* geom, const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                               const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp, float* box, float* z_where,
+                               float* attr, float* depth, float* pres, float* dmean, float* dstd, void* stream) {
+    return sweep_fwd_impl(d, order, starts, nb_offsets, image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, geom, box_mlp,
+                          enc_mlp, z_mlp, obj_mlp, box, z_where, attr, depth, pres, dmean, dstd, nullptr, false, stream);
+}
+
+extern "C" int spair_sweep_fwd_tc(const spair_sweep_dims* d, const int* order, const int* starts, const int* nb_offsets,
+                                  const float* image, const float* feat, const float* edge, const float* eps_where,
+                                  const float* eps_attr, const float* eps_depth, const float* u_pres,
+                                  const spair_box_geom* geom, const spair_sweep_mlp* box_mlp, const spair_sweep_mlp* enc_mlp,
+                                  const spair_sweep_mlp* z_mlp, const spair_sweep_mlp* obj_mlp, float* box, float* z_where,
+                                  float* attr, float* depth, float* pres, float* dmean, float* dstd, const float* wstream,
+                                  void* stream) {
+    return sweep_fwd_impl(d, order, starts, nb_offsets, image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, geom, box_mlp,
+                          enc_mlp, z_mlp, obj_mlp, box, z_where, attr, depth, pres, dmean, dstd, wstream, true, stream);
+}
+
+static bool to_mlp_bwd(const spair_sweep_mlp_bwd* m, SweepMLPBwd& out, bool need_w) {
     if (!m || !m->h0 || !m->h1 || !m->y || !m->dx || !m->dh0 || !m->dh1 || !m->dy) return false;
     for (int i = 0; i < 3; ++i) {
-        if (!m->w[i] || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
+        if ((need_w && !m->w[i]) || m->k[i] <= 0 || m->n[i] <= 0 || m->n[i] > 256) return false;
         if ((uintptr_t)m->w[i] % 16) return false;
         out.W[i] = reinterpret_cast<const float4*>(m->w[i]); out.K[i] = m->k[i]; out.N[i] = m->n[i];
     }
@@ -891,14 +1184,14 @@ static bool to_mlp_bwd(const spair_sweep_mlp_bwd* m, SweepMLPBwd& out) {
     return true;
 }
 
-extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* wf_pos,
-                               const int* nb_offsets, const float* image, const float* z_where, const float* eps_where,
-                               const float* eps_attr, const float* eps_depth, const float* u_pres, const float* wheel,
-                               const spair_box_geom* geom, const spair_sweep_mlp_bwd* box_mlp,
-                               const spair_sweep_mlp_bwd* enc_mlp, const spair_sweep_mlp_bwd* z_mlp,
-                               const spair_sweep_mlp_bwd* obj_mlp, const float* d_zw, const float* d_attr,
-                               const float* d_depth, const float* d_pres, const float* d_dmean, const float* d_dstd,
-                               void* stream) {
+static int sweep_bwd_impl(const spair_sweep_dims* d, const int* order, const int* starts, const int* wf_pos,
+                          const int* nb_offsets, const float* image, const float* z_where, const float* eps_where,
+                          const float* eps_attr, const float* eps_depth, const float* u_pres, const float* wheel,
+                          const spair_box_geom* geom, const spair_sweep_mlp_bwd* box_mlp,
+                          const spair_sweep_mlp_bwd* enc_mlp, const spair_sweep_mlp_bwd* z_mlp,
+                          const spair_sweep_mlp_bwd* obj_mlp, const float* d_zw, const float* d_attr,
+                          const float* d_depth, const float* d_pres, const float* d_dmean, const float* d_dstd,
+                          const float* wstream, bool use_tc, void* stream) {
     SPAIR_REQUIRE(d && order && starts && wf_pos && nb_offsets && image && z_where && eps_where && eps_attr && eps_depth && u_pres);
     SPAIR_REQUIRE(wheel && geom && ((uintptr_t)z_where % 16) == 0 && (d_dmean == nullptr) == (d_dstd == nullptr));
     SPAIR_REQUIRE(d->B > 0 && d->HW == d->Hc * d->Wc && d->G > 0 && d->G <= kSwMaxG && d->ipc >= 1 && d->n_wavefronts > 0);
@@ -911,17 +1204,65 @@ extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, cons
     a.order = order; a.starts = starts; a.wf_pos = wf_pos; a.image = image; a.z_where = z_where;
     a.eps_where = eps_where; a.eps_attr = eps_attr; a.eps_depth = eps_depth; a.u_pres = u_pres; a.wheel = wheel;
     a.geom = *geom;
-    SPAIR_REQUIRE(to_mlp_bwd(box_mlp, a.box) && to_mlp_bwd(enc_mlp, a.enc) && to_mlp_bwd(z_mlp, a.z) && to_mlp_bwd(obj_mlp, a.obj));
+    SPAIR_REQUIRE(to_mlp_bwd(box_mlp, a.box, !use_tc) && to_mlp_bwd(enc_mlp, a.enc, !use_tc) && to_mlp_bwd(z_mlp, a.z, !use_tc) &&
+                  to_mlp_bwd(obj_mlp, a.obj, !use_tc));
     const int E = d->A + 6, CTX = d->n_nb * E;
     SPAIR_REQUIRE(a.box.K[0] == d->F + CTX && a.box.N[2] == 8 + d->P && a.enc.K[0] == d->C * d->G * d->G && a.enc.N[2] == 2 * d->A);
     SPAIR_REQUIRE(a.z.K[0] == d->F + CTX + d->P + 4 + d->A && a.z.N[2] == 2 + d->P && a.obj.K[0] == a.z.K[0] + 1 && a.obj.N[2] == 1);
     a.encX = nullptr; a.ld_encX = 0;
     a.d_zw = d_zw; a.d_attr = d_attr; a.d_depth = d_depth; a.d_pres = d_pres; a.d_dmean = d_dmean; a.d_dstd = d_dstd;
+    const int grid = (d->B + d->ipc - 1) / d->ipc;
+    tc::Plan plan;
+    plan.n_layers = 0;
+    if (use_tc) {
+        SPAIR_REQUIRE(wstream && ((uintptr_t)wstream % 16) == 0);
+        const SweepMLPBwd* ms[4] = {&a.obj, &a.z, &a.enc, &a.box};
+        int stages = 0;
+        for (int m = 0; m < 4; ++m)
+            for (int i = 2; i >= 0; --i) {
+                plan.K[plan.n_layers] = ms[m]->N[i]; plan.M[plan.n_layers] = ms[m]->K[i];
+                // more feature tiles than one accumulator group: the layer's activation chunks must all stay resident
+                SPAIR_REQUIRE((ms[m]->K[i] + 127) / 128 <= tc::kTileGroup || (ms[m]->N[i] + tc::kChunkK - 1) / tc::kChunkK <= tc::kXSlots);
+                stages += tc::stages_of(ms[m]->N[i], ms[m]->K[i]);
+                ++plan.n_layers;
+            }
+        const size_t smem = 1024 + tc::kRingBytes + tc::kBarBytes +
+                            sizeof(float) * (size_t)(kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) + sizeof(int) * 3 * kSwRows;
+        static size_t smem_set_tc[kMaxDevices] = {0};
+        if (ensure_dynamic_smem(sweep_bwd_kernel<true>, smem, smem_set_tc) != cudaSuccess) return (int)cudaGetLastError();
+        sweep_bwd_kernel<true><<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(a, plan, wstream, stages);
+        SPAIR_LAUNCH_CHECK();
+    }
     const size_t smem = sizeof(float) * (size_t)(kSwPart + 3 * kSwRows * kSwHP + kSwRows * 64 + kSwMaxG + kSwRows * 4) +
                         sizeof(int) * 3 * kSwRows;
     static size_t smem_set[kMaxDevices] = {0};
-    if (ensure_dynamic_smem(sweep_bwd_kernel, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
-    const int grid = (d->B + d->ipc - 1) / d->ipc;
-    sweep_bwd_kernel<<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a);
+    if (ensure_dynamic_smem(sweep_bwd_kernel<false>, smem, smem_set) != cudaSuccess) return (int)cudaGetLastError();
+    sweep_bwd_kernel<false><<<grid, kSwThreads, smem, (cudaStream_t)stream>>>(a, plan, nullptr, 0);
     SPAIR_LAUNCH_CHECK();
+}
+
+extern "C" int spair_sweep_bwd(const spair_sweep_dims* d, const int* order, const int* starts, const int* wf_pos,
+                               const int* nb_offsets, const float* image, const float* z_where, const float* eps_where,
+                               const float* eps_attr, const float* eps_depth, const float* u_pres, const float* wheel,
+                               const spair_box_geom* geom, const spair_sweep_mlp_bwd* box_mlp,
+                               const spair_sweep_mlp_bwd* enc_mlp, const spair_sweep_mlp_bwd* z_mlp,
+                               const spair_sweep_mlp_bwd* obj_mlp, const float* d_zw, const float* d_attr,
+                               const float* d_depth, const float* d_pres, const float* d_dmean, const float* d_dstd,
+                               void* stream) {
+    return sweep_bwd_impl(d, order, starts, wf_pos, nb_offsets, image, z_where, eps_where, eps_attr, eps_depth, u_pres, wheel,
+                          geom, box_mlp, enc_mlp, z_mlp, obj_mlp, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd, nullptr, false,
+                          stream);
+}
+
+extern "C" int spair_sweep_bwd_tc(const spair_sweep_dims* d, const int* order, const int* starts, const int* wf_pos,
+                                  const int* nb_offsets, const float* image, const float* z_where, const float* eps_where,
+                                  const float* eps_attr, const float* eps_depth, const float* u_pres, const float* wheel,
+                                  const spair_box_geom* geom, const spair_sweep_mlp_bwd* box_mlp,
+                                  const spair_sweep_mlp_bwd* enc_mlp, const spair_sweep_mlp_bwd* z_mlp,
+                                  const spair_sweep_mlp_bwd* obj_mlp, const float* d_zw, const float* d_attr,
+                                  const float* d_depth, const float* d_pres, const float* d_dmean, const float* d_dstd,
+                                  const float* wstream, void* stream) {
+    return sweep_bwd_impl(d, order, starts, wf_pos, nb_offsets, image, z_where, eps_where, eps_attr, eps_depth, u_pres, wheel,
+                          geom, box_mlp, enc_mlp, z_mlp, obj_mlp, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd, wstream, true,
+                          stream);
 }

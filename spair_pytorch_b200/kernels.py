@@ -100,6 +100,10 @@ _SIGNATURES = {
     "spair_sweep_pack_weights": [_P, _I, _P],
     "spair_sweep_fwd": [_P] * 23 + [_P],
     "spair_sweep_bwd": [_P] * 23 + [_P],
+    "spair_sweep_tc_stream_floats": [_P, _P, _I, _I],
+    "spair_sweep_tc_pack": [_P, _P, _P, _I, _P, _P, _P],
+    "spair_sweep_fwd_tc": [_P] * 24 + [_P],
+    "spair_sweep_bwd_tc": [_P] * 24 + [_P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -107,7 +111,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 RENDER_MAX_TEXELS, RENDER_MAX_CHANNELS = 1024, 4   # spair_render_fwd/bwd: G*G <= 1024, C <= 4 (csrc/render.cu)
 NUM_SMS = 148          # kSMs of csrc/common.cuh (B200: 2 dies x 74 SMs)
 MAX_NEIGHBOURS = 12   # SPAIR_MAX_NEIGHBOURS of include/spair_b200.h (N_LOOKBACK <= 2)
-ABI_VERSION = 3       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
+ABI_VERSION = 4       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
 
 
 def lib() -> ctypes.CDLL:
@@ -151,6 +155,7 @@ def base_grid(n: int) -> torch.Tensor:
 
 # kernels launched per C-ABI call (render_bwd = prep + object kernel; paste_bwd's memset is not a kernel)
 _LAUNCHES_PER_CALL = {"spair_render_bwd": 2, "spair_base_grid": 0, "spair_sweep_max_rows": 0, "spair_stem_bwd_ctas": 0,
+                      "spair_sweep_tc_stream_floats": 0,
                       "spair_stem_conv_bwd": 2}
 LAUNCH_COUNT = 0
 
@@ -548,11 +553,37 @@ class PackedSweepWeights:
             _check(lib().spair_sweep_pack_weights(arr, len(weights), _stream()), "spair_sweep_pack_weights")
 
 
+class PackedSweepWeightsTC:
+    """The weight streams of the tensor-core sweeps (``spair_sweep_tc_pack``): all 12 ``nn.Linear`` weights [N, K] (order
+    box0 .. obj2) split into TF32 hi / lo, swizzled and laid out in the order the kernels consume them, one stream per
+    direction, filled by one launch.  Keep this object alive while kernels use the streams."""
+
+    def __init__(self, weights):
+        assert len(weights) == 12, "four MLPs of two hidden layers + output"
+        for w in weights:
+            require_cuda(w, "weight")
+        self.shapes = [(int(w.shape[0]), int(w.shape[1])) for w in weights]
+        n = (ctypes.c_int * 12)(*[s[0] for s in self.shapes])
+        k = (ctypes.c_int * 12)(*[s[1] for s in self.shapes])
+        nf = lib().spair_sweep_tc_stream_floats(n, k, 12, 0)
+        nb = lib().spair_sweep_tc_stream_floats(n, k, 12, 1)
+        if nf <= 0 or nb <= 0:
+            raise SpairKernelError("spair_sweep_tc_stream_floats rejected the layer list")
+        self.flat = torch.empty(nf + nb, device=weights[0].device, dtype=torch.float32)
+        self.fwd, self.bwd = self.flat[:nf], self.flat[nf:]
+        self._sources = [_contig(w.detach(), "weight") for w in weights]
+        ptrs = (ctypes.c_void_p * 12)(*[_ptr(w) for w in self._sources])
+        with torch.cuda.device(weights[0].device):
+            _check(lib().spair_sweep_tc_pack(ptrs, n, k, 12, _ptr(self.fwd), _ptr(self.bwd), _stream()), "spair_sweep_tc_pack")
+
+
 def sweep_mlp_desc(packed, first, biases, X, H0, H1, Y) -> SweepMLP:
     """packed: PackedSweepWeights; layers first .. first+2 are the two hidden layers and the output layer."""
     m = SweepMLP()
     for i, b in enumerate(biases):
-        m.wt[i], m.b[i] = _ptr(packed.fwd[first + i]), _ptr(_contig(b, "bias"))
+        # tensor-core sweep: the unpacked weight (re-evaluation of ReLU pre-activations near zero), else the fwd-packed one
+        m.wt[i] = _ptr(packed._sources[first + i]) if isinstance(packed, PackedSweepWeightsTC) else _ptr(packed.fwd[first + i])
+        m.b[i] = _ptr(_contig(b, "bias"))
         m.n[i], m.k[i] = packed.shapes[first + i]
     m.x, m.ld_x, m.h0, m.h1, m.y = _ptr(X, "X"), _ld(X), _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), \
         _ptr(_contig(Y, "Y"))
@@ -560,22 +591,25 @@ def sweep_mlp_desc(packed, first, biases, X, H0, H1, Y) -> SweepMLP:
 
 
 def sweep_fwd(dims: SweepDims, order, starts, offsets, image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, geom,
-              mlps, box, z_where, attr, depth, pres, dmean, dstd):
+              mlps, box, z_where, attr, depth, pres, dmean, dstd, tc_stream=None):
     arr, _ = _offsets_array(offsets)
     for t in (image, feat, edge, eps_where, eps_attr, eps_depth, u_pres, box, z_where, attr, depth, pres, dmean, dstd):
         _contig(t, "sweep tensor")
-    _check(lib().spair_sweep_fwd(ctypes.byref(dims), _iptr(order), _iptr(starts), arr, _ptr(image), _ptr(feat), _ptr(edge),
-                                 _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), ctypes.byref(geom),
-                                 ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]), ctypes.byref(mlps[3]),
-                                 _ptr(box), _ptr(z_where), _ptr(attr), _ptr(depth), _ptr(pres), _ptr(dmean), _ptr(dstd),
-                                 _stream()), "spair_sweep_fwd")
+    args = (ctypes.byref(dims), _iptr(order), _iptr(starts), arr, _ptr(image), _ptr(feat), _ptr(edge),
+            _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), ctypes.byref(geom),
+            ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]), ctypes.byref(mlps[3]),
+            _ptr(box), _ptr(z_where), _ptr(attr), _ptr(depth), _ptr(pres), _ptr(dmean), _ptr(dstd))
+    if tc_stream is not None:
+        _check(lib().spair_sweep_fwd_tc(*args, _ptr(tc_stream), _stream()), "spair_sweep_fwd_tc")
+    else:
+        _check(lib().spair_sweep_fwd(*args, _stream()), "spair_sweep_fwd")
 
 
 def sweep_mlp_bwd_desc(packed, first, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBwd:
     """packed: PackedSweepWeights; layers first .. first+2 are the two hidden layers and the output layer."""
     m = SweepMLPBwd()
     for i in range(3):
-        m.w[i] = _ptr(packed.bwd[first + i])
+        m.w[i] = None if isinstance(packed, PackedSweepWeightsTC) else _ptr(packed.bwd[first + i])
         m.n[i], m.k[i] = packed.shapes[first + i]
     m.h0, m.h1, m.y = _ptr(_contig(H0, "H0")), _ptr(_contig(H1, "H1")), _ptr(_contig(Y, "Y"))
     m.dx, m.ld_dx = _ptr(dX, "dX"), _ld(dX)
@@ -584,15 +618,18 @@ def sweep_mlp_bwd_desc(packed, first, H0, H1, Y, dX, dH0, dH1, dY) -> SweepMLPBw
 
 
 def sweep_bwd(dims: SweepDims, order, starts, wf_pos, offsets, image, z_where, eps_where, eps_attr, eps_depth, u_pres, wheel,
-              geom, mlps, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd):
+              geom, mlps, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd, tc_stream=None):
     arr, _ = _offsets_array(offsets)
     for t in (image, z_where, eps_where, eps_attr, eps_depth, u_pres, d_zw, d_attr, d_depth, d_pres, d_dmean, d_dstd):
         _contig(t, "sweep tensor")
-    _check(lib().spair_sweep_bwd(ctypes.byref(dims), _iptr(order), _iptr(starts), _iptr(wf_pos), arr, _ptr(image),
-                                 _ptr(z_where), _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), _ptr(wheel),
-                                 ctypes.byref(geom), ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]),
-                                 ctypes.byref(mlps[3]), _ptr(d_zw), _ptr(d_attr), _ptr(d_depth), _ptr(d_pres), _ptr(d_dmean),
-                                 _ptr(d_dstd), _stream()), "spair_sweep_bwd")
+    args = (ctypes.byref(dims), _iptr(order), _iptr(starts), _iptr(wf_pos), arr, _ptr(image),
+            _ptr(z_where), _ptr(eps_where), _ptr(eps_attr), _ptr(eps_depth), _ptr(u_pres), _ptr(wheel),
+            ctypes.byref(geom), ctypes.byref(mlps[0]), ctypes.byref(mlps[1]), ctypes.byref(mlps[2]),
+            ctypes.byref(mlps[3]), _ptr(d_zw), _ptr(d_attr), _ptr(d_depth), _ptr(d_pres), _ptr(d_dmean), _ptr(d_dstd))
+    if tc_stream is not None:
+        _check(lib().spair_sweep_bwd_tc(*args, _ptr(tc_stream), _stream()), "spair_sweep_bwd_tc")
+    else:
+        _check(lib().spair_sweep_bwd(*args, _stream()), "spair_sweep_bwd")
 
 
 # ----------------------------------------------------------------------------------------

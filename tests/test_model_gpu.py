@@ -235,3 +235,46 @@ def test_fused_forward_sweep_equals_per_wavefront_path(name, B):
     for k in a["grads"]:      # norm-wise: some of these tensors are dominated by fp32 cancellation noise
         rel = float((a["grads"][k] - b["grads"][k]).norm() / b["grads"][k].norm().clamp(min=1e-12))
         assert rel <= 5e-2, "grad %s differs by %.3e (relative L2) between the two forward paths" % (k, rel)
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 5), ("A", 4), ("A", 3), ("C", 3), ("rgb64", 2), ("tiny_lb2", 3), ("D", 1)])
+def test_tensor_core_sweep_equals_simt_sweep(name, B, monkeypatch):
+    """The fused sweeps with their dense layers on tcgen05 (csrc/sweep_tc.cuh: split-precision TF32 MMAs, weights streamed
+    by bulk async copies; opt-in with SPAIR_SWEEP_TC=1) against the same kernels with fp32 SIMT dense layers (the default) on
+    the same inputs and noise: every activation / gradient buffer of the four per-cell MLPs (reference modules.py:124-165 inside
+    the loop of models.py:68-117) agrees to the split-precision rounding forward (~1e-6 of the buffer's scale).  The
+    backward buffers see the same arithmetic but ALSO the forward's 1e-6 differences amplified by the renderer's loss
+    (BCE gradients ~ 1 / recon): a few 1e-3 of their scale on these inputs, which is why the
+    tensor-core sweep is opt-in and not the parity path.  B = 4 runs two images per CTA, B = 3 leaves a
+    CTA with one image, D has more feature tiles (3 x 28 x 28 inputs) than one accumulator group."""
+    from oracle import spair_oracle as so
+    net = helpers.build_model(name, DEV)
+    cfg = helpers.oracle_config(name)
+    x = so.scattered_sprites(B, cfg.image_shape, seed=33, sprite_px=(6, 14)).to(DEV)
+    noise = so.random_noise(torch.Generator().manual_seed(6), B, cfg.grid, cfg.n_attr)
+    results = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("SPAIR_SWEEP_TC", tc)
+        net._plan = None
+        net(x[:1], 1001)
+        net.set_noise(noise.eps_where, noise.eps_attr, noise.eps_depth, noise.u_pres)
+        for p in net.parameters():
+            p.grad = None
+        loss = net(x, 1001)[0]
+        loss.backward()
+        bufs = {}
+        for mname, m in zip(("box", "enc", "z", "obj"), net._plan.last_mlps):
+            for bname, t in (("X", m.X), ("H0", m.H[0]), ("H1", m.H[1]), ("Y", m.Y), ("dX", m.dX), ("dH0", m.dH[0]),
+                             ("dH1", m.dH[1]), ("dY", m.dY)):
+                bufs[mname + "." + bname] = t.detach().clone()
+        results.append((loss.detach().clone(), bufs, {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    (l0, b0, g0), (l1, b1, g1) = results
+    assert abs(float(l0 - l1)) <= 1e-5 * abs(float(l0))
+    for k in b0:
+        scale = float(b0[k].abs().max())
+        tol = (2e-5 if k.split(".")[1].startswith("d") is False else 1e-2) * max(scale, 1e-12)
+        err = float((b0[k] - b1[k]).abs().max())
+        assert err <= tol, "%s: tensor-core vs SIMT sweep differ by %.3e (scale %.3e)" % (k, err, scale)
+    for k in g0:
+        rel = float((g0[k] - g1[k]).norm() / g0[k].norm().clamp(min=1e-12))
+        assert rel <= 1e-2, "grad %s differs by %.3e (relative L2) between the tensor-core and the SIMT sweep" % (k, rel)

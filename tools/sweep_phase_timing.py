@@ -24,7 +24,10 @@ NAMES = {0: 'fwd gather+tables', 1: 'fwd box mlp', 2: 'fwd box head', 3: 'fwd gl
          20: 'fwd accumulate', 21: 'fwd partial store+sync', 22: 'fwd finalize+sync',
          30: 'bwd ctx+pres head', 31: 'bwd obj mlp', 32: 'bwd depth head', 33: 'bwd z mlp', 34: 'bwd attr head', 35: 'bwd enc mlp',
          36: 'bwd box head', 37: 'bwd box mlp', 38: 'bwd glimpse grad', 40: 'bwd accumulate', 41: 'bwd partial+sync',
-         42: 'bwd finalize+sync'}
+         42: 'bwd finalize+sync',
+         13: 'fwd layer1->2 boundary (tensor-core path: 11 = layer 0, 13 = layer 1, 12 = layer 2)',
+         43: 'bwd tc stage dY', 44: 'bwd tc layer 2', 45: 'bwd tc layer 1', 46: 'bwd tc layer 0'}
+# tensor-core path (default): 20 / 40 = waiting for the accumulator, 21 / 41 = the rest of the epilogue
 
 
 def main():
@@ -35,6 +38,8 @@ def main():
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     net = helpers.build_model(name).cuda()
     x = torch.rand(batch, *net.image_shape, device='cuda')
+    if os.environ.get("TC_DEBUG_FLAGS"):     # instrumented builds: 1 = no weight copies, 2 = no MMAs (timing only, garbage results)
+        lib.spair_debug_sweep_tc_flags(int(os.environ["TC_DEBUG_FLAGS"]))
     buf = (ctypes.c_longlong * 64)()
     for _ in range(3):
         net(x, 1000)[0].backward()
