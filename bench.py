@@ -287,10 +287,15 @@ def kernel_roofline(net, x, steps=20):
         if sweep_ms[k]:
             ms = statistics.mean(sweep_ms[k])
             tf = 2 * macs * N / (ms * 1e-3) / 1e12
+            mode = os.environ.get("SPAIR_SWEEP_TC", "bwd")
+            on_tc = mode == "1" or (mode == "bwd" and k == "bwd")
             out[label] = {"ms": ms, "flops": 2 * macs * N, "achieved": tf, "frac": tf / fpeak, "bound": "fp32",
                           "unit": "TFLOP/s", "peak": fpeak,
+                          "dense_layers": "tcgen05 kind::tf32, hi/lo split (csrc/sweep_tc.cuh)" if on_tc else "fp32 SIMT FFMA",
                           "note": "persistent fused cell sweep (%s): context + 4 MLPs + heads + glimpse for all wavefronts "
-                                  "in one launch; the chain of %d dependent wavefronts x 12 layers bounds it, not the FFMA rate"
+                                  "in one launch; the chain of %d dependent wavefronts x 12 layers bounds it (tensor-core "
+                                  "variant: the ~67-cycle issue interval of a tcgen05.mma, tensor pipe 6 %% busy), not the "
+                                  "arithmetic rate; algorithmic fp32 FLOPs against the fp32 FFMA peak either way"
                                   % (k, plan.schedule.n_wavefronts)}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same
     # kernels at this shape (B=256, C=1, I=128, 121 cells, G=28)
@@ -564,7 +569,7 @@ def run_ours(args):
             "config": {"workload": "BASELINE %s, batch %d per GPU, procedural scattered sprites, step = zero_grad+fwd+bwd+Adam%s"
                                    % (workload_name(args.config), B, "+NCCL grad allreduce" if world > 1 else ""),
                        "per_gpu_batch": B, "global_batch": world * B, "objects_per_image": HW, "global_step": STEP0,
-                       "parallelism": "dp%d" % world, "tf32": "3xTF32 split (fp32-accurate) tcgen05 GEMMs for the decoder MLP and the weight gradients; sweep MLPs fp32 SIMT; "
+                       "parallelism": "dp%d" % world, "tf32": "3xTF32 split (fp32-accurate) tcgen05 GEMMs for the decoder MLP, the backbone tail, the weight gradients and the dense layers of the BACKWARD sweep; forward sweep MLPs fp32 SIMT; "
                                                               "cuDNN/cuBLAS TF32 off",
                        "launch": "eager" if args.eager else "fwd+bwd replayed from one CUDA graph; allreduce + fused Adam eager",
                        "l2": "per-step working set (~2.3 KB x %d objects x fwd+bwd buffers, > 1 GB) exceeds the 126 MB L2; "

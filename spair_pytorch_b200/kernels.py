@@ -558,19 +558,20 @@ class PackedSweepWeightsTC:
     box0 .. obj2) split into TF32 hi / lo, swizzled and laid out in the order the kernels consume them, one stream per
     direction, filled by one launch.  Keep this object alive while kernels use the streams."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, forward=True, backward=True):
         assert len(weights) == 12, "four MLPs of two hidden layers + output"
         for w in weights:
             require_cuda(w, "weight")
         self.shapes = [(int(w.shape[0]), int(w.shape[1])) for w in weights]
         n = (ctypes.c_int * 12)(*[s[0] for s in self.shapes])
         k = (ctypes.c_int * 12)(*[s[1] for s in self.shapes])
-        nf = lib().spair_sweep_tc_stream_floats(n, k, 12, 0)
-        nb = lib().spair_sweep_tc_stream_floats(n, k, 12, 1)
-        if nf <= 0 or nb <= 0:
+        nf = lib().spair_sweep_tc_stream_floats(n, k, 12, 0) if forward else 0
+        nb = lib().spair_sweep_tc_stream_floats(n, k, 12, 1) if backward else 0
+        if nf < 0 or nb < 0 or nf + nb == 0:
             raise SpairKernelError("spair_sweep_tc_stream_floats rejected the layer list")
         self.flat = torch.empty(nf + nb, device=weights[0].device, dtype=torch.float32)
-        self.fwd, self.bwd = self.flat[:nf], self.flat[nf:]
+        self.fwd = self.flat[:nf] if forward else None       # a direction that is not asked for is not packed
+        self.bwd = self.flat[nf:] if backward else None
         self._sources = [_contig(w.detach(), "weight") for w in weights]
         ptrs = (ctypes.c_void_p * 12)(*[_ptr(w) for w in self._sources])
         with torch.cuda.device(weights[0].device):
