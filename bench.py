@@ -325,8 +325,8 @@ def kernel_roofline(net, x, steps=20):
 
 # per-launch DRAM traffic (bytes read + written) from `ncu --set full` captures at config B; (bytes, source)
 NCU_TRAFFIC = {
-    "sweep_fwd": (48570368 + 383217000, "profiles/r02_kernels_full.md (ncu --set full, per launch)"),
-    "sweep_bwd": (196361728 + 365944000, "profiles/r02_kernels_full.md (ncu --set full, per launch)"),
+    "sweep_fwd": (48197888 + 383831808, "profiles/r02_kernels_full.md (ncu --set full, per launch; fp32 SIMT dense layers)"),
+    "sweep_bwd": (200129536 + 375443712, "profiles/r02_kernels_full.md (ncu --set full, per launch; tcgen05 dense layers)"),
     "render_bwd": (228634368 + 159153000, "profiles/r02_kernels_full.md (ncu --set full, per launch, texel-record input)"),
     "render_fwd": (197374976 + 23060000, "profiles/r02_kernels_full.md (ncu --set full, per launch, texel-record input)"),
     "glimpse_fwd": (18863616 + 40622080, "profiles/r02_glimpse_full.md (ncu --set full, per launch)"),
