@@ -574,10 +574,13 @@ class CellSweepFunction(torch.autograd.Function):
             # Dense layers of the sweeps on the tensor cores (csrc/sweep_tc.cuh; split-precision TF32: ~1e-6 relative instead
             # of ~1e-7).  Default: the BACKWARD sweep only — gradients tolerate 1e-6, whereas a 1e-6 error in the forward
             # latents is amplified by this model's loss (BCE gradients ~ 1 / recon) beyond rtol 1e-4 on one golden case
-            # (DESIGN.md section 5), so the forward stays on the fp32 SIMT layers.  SPAIR_SWEEP_TC=1: both sweeps (fastest);
-            # SPAIR_SWEEP_TC=0: neither.
-            mode = _os.environ.get("SPAIR_SWEEP_TC", "bwd")
-            tc_fwd, tc_bwd = mode == "1", mode in ("1", "bwd")
+            # (DESIGN.md section 5), so the forward stays on the fp32 SIMT layers.  The tensor-core layers cost the same for
+            # 1 or 16 rows (MMA issue interval) while the SIMT layers scale with the rows, so the default ("auto") takes
+            # them only when a CTA has >= 12 rows per wavefront (measured: 16 rows 2.39 vs 2.65 ms, 8 rows 2.48 vs 2.27 ms).
+            # SPAIR_SWEEP_TC=1: both sweeps; =bwd: backward always; =0: neither.
+            mode = _os.environ.get("SPAIR_SWEEP_TC", "auto")
+            tc_fwd = mode == "1"
+            tc_bwd = mode in ("1", "bwd") or (mode == "auto" and s.max_cells * ipc >= 12)
             weights = [w for m in mlps for w in m.W]
             packed = None if (tc_fwd and tc_bwd) else K.PackedSweepWeights(weights)     # one launch each; kept for backward
             packed_tc = K.PackedSweepWeightsTC(weights, forward=tc_fwd, backward=tc_bwd) if (tc_fwd or tc_bwd) else None
