@@ -237,7 +237,7 @@ def test_fused_forward_sweep_equals_per_wavefront_path(name, B):
         assert rel <= 5e-2, "grad %s differs by %.3e (relative L2) between the two forward paths" % (k, rel)
 
 
-@pytest.mark.parametrize("name,B", [("tiny", 5), ("A", 4), ("A", 3), ("C", 3), ("rgb64", 2), ("tiny_lb2", 3), ("D", 1)])
+@pytest.mark.parametrize("name,B", [("tiny", 5), ("tiny", 149), ("A", 4), ("A", 3), ("C", 3), ("rgb64", 2), ("tiny_lb2", 3), ("D", 1)])
 def test_tensor_core_sweep_equals_simt_sweep(name, B, monkeypatch):
     """The fused sweeps with their dense layers on tcgen05 (csrc/sweep_tc.cuh: split-precision TF32 MMAs, weights streamed
     by bulk async copies; opt-in with SPAIR_SWEEP_TC=1) against the same kernels with fp32 SIMT dense layers (the default) on
@@ -245,8 +245,9 @@ def test_tensor_core_sweep_equals_simt_sweep(name, B, monkeypatch):
     the loop of models.py:68-117) agrees to the split-precision rounding forward (~1e-6 of the buffer's scale).  The
     backward buffers see the same arithmetic but ALSO the forward's 1e-6 differences amplified by the renderer's loss
     (BCE gradients ~ 1 / recon): a few 1e-3 of their scale on these inputs, which is why the
-    tensor-core sweep is opt-in and not the parity path.  B = 4 runs two images per CTA, B = 3 leaves a
-    CTA with one image, D has more feature tiles (3 x 28 x 28 inputs) than one accumulator group."""
+    tensor-core FORWARD sweep is opt-in and not the parity path.  B = 149 (> 148 SMs) runs two images per CTA with a single
+    image in the last CTA, the other cases one image per CTA; D has more feature tiles (3 x 28 x 28 inputs) than one
+    accumulator group."""
     from oracle import spair_oracle as so
     net = helpers.build_model(name, DEV)
     cfg = helpers.oracle_config(name)
