@@ -13,9 +13,10 @@
 //     operand tiles (128 x 32 floats, 128-byte swizzle, hi then lo = 32 KB per stage), laid out in consumption order: a
 //     producer thread streams the whole sequence with plain bulk async copies (cp.async.bulk, SASS UBLKCP) through a
 //     3-stage mbarrier ring and runs ahead ACROSS layer boundaries, so a layer never starts with a cold L2 round trip;
-//   * one MMA-issuer thread walks the static layer plan; the workers convert their activations into B tiles (first layer:
-//     from the global input rows; hidden layers: straight from the epilogue registers) and hand them over through a
-//     3-slot ring; tcgen05.commit frees weight stages / activation slots and publishes the accumulator.
+//   * two MMA-issuer threads walk the static layer plan, alternating over the k-blocks of a layer (the issue interval of a
+//     tcgen05.mma, not its execution, is what a stage costs); the workers convert their activations into B tiles (first
+//     layer: from the global input rows; hidden layers: straight from the epilogue registers) and hand them over through
+//     a 3-slot ring; tcgen05.commit frees weight stages / activation slots and publishes the accumulators.
 // Hidden activations never exist in row-major form on chip: the epilogue of layer l (tcgen05.ld -> bias -> ReLU / mask)
 // writes layer l+1's swizzled hi / lo operand rows and the global copy the weight-gradient GEMMs need.
 #pragma once
@@ -31,7 +32,7 @@ namespace tc {
 
 #ifdef SW_TIMING
 // diagnostics of instrumented builds only (results are garbage): 1 = the producer signals stages without copying,
-// 2 = the MMA thread commits without issuing MMAs
+// 2 = the MMA threads commit without issuing MMAs (spair_debug_sweep_tc_flags; tools/sweep_phase_timing.py TC_DEBUG_FLAGS)
 __device__ int g_tc_debug;
 #define TC_DEBUG(flag) (g_tc_debug & (flag))
 #else
@@ -57,7 +58,7 @@ constexpr int kXSlots = 3;
 constexpr int kChunkK = kChunkKB * 32;   // reduction indices per activation chunk
 constexpr int kTmemCols = 512;
 constexpr int kTileCols = 32 * kAccs;    // every accumulator: 16 columns hi*hi + lo*hi, 16 columns hi*lo
-constexpr int kTileGroup = kTmemCols / kTileCols;   // 128-feature tiles per accumulator group (5)
+constexpr int kTileGroup = kTmemCols / kTileCols;   // 128-feature tiles per accumulator group (8)
 constexpr int kMaxLayers = 12;
 constexpr int kRingBytes = kWStages * kStageBytes + kXSlots * kSlotBytes;
 constexpr int kBarBytes = 256;
