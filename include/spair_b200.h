@@ -26,7 +26,7 @@ extern "C" {
 
 #define SPAIR_ERR_INVALID (-1)
 #define SPAIR_MAX_NEIGHBOURS 12
-#define SPAIR_ABI_VERSION 4   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows; 3: tcgen05 GEMM; 4: tcgen05 sweep */
+#define SPAIR_ABI_VERSION 5   /* 2: packed sweep weights, sweep backward, stem, broadcast_rows; 3: tcgen05 GEMM; 4: tcgen05 sweep; 5: pre-split GEMM weights */
 
 int spair_abi_version(void);
 
@@ -416,7 +416,15 @@ int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb,
                      pre-activation is within the product's rounding error of zero are listed in kink_ws ([0] = counter,
                      then up to kink_cap entries) and re-evaluated with float64 accumulation by a second launch, so that
                      the ReLU takes the exact branch (the reference's gradient below the layer depends on it); NULL / 0: off */,
+                 const float* B_hi, const float* B_lo /* both NULL, or the TF32 hi / lo planes of B (a weight matrix; same shape
+                     and pitch; spair_split_tf32).  The kernel then loads the planes and only splits the A tiles — half of the
+                     splitter work, identical results; B itself is still read by the exact-ReLU pass */,
                  void* stream);
+
+/* hi[i] = src[i] rounded to TF32 (nearest, ties away; stored as fp32), lo[i] = TF32(src[i] - hi[i]): the operand split the
+ * GEMM kernels otherwise perform on every tile, done once per step for the weight matrices (nn.Linear / nn.Conv2d
+ * weights of reference modules.py:44-66,124-165, models.py:165). */
+int spair_split_tf32(const float* src, float* hi, float* lo, int n, void* stream);
 
 /* Implicit-GEMM convolution of the backbone tail on a channels-last input x [B,H,W,C] (k x k window, stride s, no
  * padding; reference modules.py:44-66), the patch matrix read tile by tile with TMA im2col loads instead of being
@@ -425,7 +433,9 @@ int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb,
  * C must be a multiple of 32.  epilogue / workspace / splits / kink_ws as in spair_gemm3x. */
 int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int stride, int mode, const float* other,
                       int ld_other, float* out, int ldc, int Cout, const float* bias, int epilogue, float* workspace,
-                      int splits, unsigned* kink_ws, int kink_cap, void* stream);
+                      int splits, unsigned* kink_ws, int kink_cap,
+                      const float* w_hi, const float* w_lo /* mode 1 only: NULL, or the TF32 planes of the weights `other` */,
+                      void* stream);
 
 /* Input gradient of the same convolution (k % stride == 0, Cout % 32 == 0) without a d_col matrix: stride*stride stride-1
  * sub-convolutions over dy (one GEMM per output parity class; the epilogue scatters the rows to their pixels of dx).
@@ -433,7 +443,8 @@ int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int str
  * wc[py*stride+px][c][(kh*T + kw)*Cout + co] = w[co][c][py + stride*(T-1-kh)][px + stride*(T-1-kw)];
  * dx [B,H,W,Cin] is fully overwritten. */
 int spair_conv_dgrad3x(const float* dy, int B, int H, int W, int Cin, int k, int stride, int Cout, const float* wc,
-                       float* dx, void* stream);
+                       float* dx, const float* wc_hi, const float* wc_lo /* NULL, or the TF32 planes of the class weights wc */,
+                       void* stream);
 
 /* Patch gather / transposed gather around spair_gemm3x for the k x k / stride s convolutions of the backbone tail
  * (reference modules.py:44-66), channels-last activations.  col[m][(kh*k + kw)*C + c] = x[b][s*oy+kh][s*ox+kw][c] with

@@ -124,6 +124,8 @@ struct Params {
     int period;           // texel decode: channels per texel (C + 1)
     float s_colour, s_alpha, b_alpha;
     int debug;            // diagnostics (SPAIR_GEMM_DEBUG): 1 = splitters skip their work, 2 = one MMA per k-step, 4 = no stores
+    int b_presplit;       // the B operand (a weight matrix) arrives already split: map_b = its TF32 hi plane, map_b2 = its lo plane;
+                          // the producer loads both and the splitters only convert the A tile (half of their work)
     int acc_split;        // 1, or 4 (BN <= 128): k-block j accumulates into TMEM accumulator j % 4, summed in the epilogue
     // implicit-GEMM convolution on a channels-last input (reference Backbone, modules.py:44-66): 0 = plain GEMM;
     // 1 = the A operand is the patch matrix of x, read by TMA im2col (forward, rows = output pixels);
@@ -153,7 +155,8 @@ struct Cfg {
 
 template <int BN, bool A_K, bool B_K>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_b2, const Params p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -223,7 +226,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     mbar_wait(bar_empty(stage), phase ^ 1);
                     // (weight gradient of a convolution: a last column tile may hold fewer than BN / 32 patch atoms)
                     const int b_atoms = p.conv == 2 ? min(BN / 32, (p.N - nt * BN + 31) / 32) : BN / 32;
-                    mbar_expect_tx(bar_full(stage), C::kStageA + (p.conv == 2 ? b_atoms * 4096 : C::kStageB));
+                    mbar_expect_tx(bar_full(stage), C::kStageA + (p.conv == 2 ? b_atoms * 4096 : C::kStageB) + (p.b_presplit ? C::kStageB : 0));
                     const int k0 = k_base + kb * BK;
                     if (p.conv == 1) {
                         // k-block -> (tap, 32-channel block); tile row 0 -> (image, oy, ox); 128 pixels in one instruction
@@ -249,9 +252,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         }
                     } else if (B_K) {
                         tma_load_2d(b_hi(stage), &map_b, bar_full(stage), k0, nt * BN);
+                        if (p.b_presplit) tma_load_2d(b_lo(stage), &map_b2, bar_full(stage), k0, nt * BN);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(stage) + j * 4096, &map_b, bar_full(stage), nt * BN + 32 * j, k0);
+                        if (p.b_presplit) {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_lo(stage) + j * 4096, &map_b2, bar_full(stage), nt * BN + 32 * j, k0);
+                        }
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -323,7 +331,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 mbar_wait(bar_full(stage), phase);
                 const uint32_t s0 = a_hi(stage);
 #pragma unroll 4
-                for (int c = t; c < ((p.debug & 1) ? 0 : kChunks); c += kSplitWarps * 32) {
+                for (int c = t; c < ((p.debug & 1) ? 0 : (p.b_presplit ? C::kStageA / 16 : kChunks)); c += kSplitWarps * 32) {
                     const uint32_t addr = s0 + c * 16;
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -593,22 +601,44 @@ static bool make_im2col_map(CUtensorMap* map, const float* x, int B, int H, int 
 }
 
 template <int BN, bool A_K, bool B_K>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const Params& p, cudaStream_t stream) {
     static size_t cache[kMaxDevices] = {};
     auto kern = gemm3x_kernel<BN, A_K, B_K>;
     cudaError_t e = ensure_dynamic_smem(kern, Cfg<BN>::kSmem, cache);
     if (e != cudaSuccess) return (int)e;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
     const int n_work = m_tiles * n_tiles * p.splits;
-    kern<<<n_work < kSMs ? n_work : kSMs, kThreads, Cfg<BN>::kSmem, stream>>>(ma, mb, p);
+    kern<<<n_work < kSMs ? n_work : kSMs, kThreads, Cfg<BN>::kSmem, stream>>>(ma, mb, mb2, p);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <int BN>
-static int launch_major(bool a_k, bool b_k, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
-    if (a_k) return b_k ? launch<BN, true, true>(ma, mb, p, st) : launch<BN, true, false>(ma, mb, p, st);
-    return b_k ? launch<BN, false, true>(ma, mb, p, st) : launch<BN, false, false>(ma, mb, p, st);
+static int launch_major(bool a_k, bool b_k, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const Params& p,
+                        cudaStream_t st) {
+    if (a_k) return b_k ? launch<BN, true, true>(ma, mb, mb2, p, st) : launch<BN, true, false>(ma, mb, mb2, p, st);
+    return b_k ? launch<BN, false, true>(ma, mb, mb2, p, st) : launch<BN, false, false>(ma, mb, mb2, p, st);
+}
+
+static int launch_bn(int bn, bool a_k, bool b_k, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const Params& p,
+                     cudaStream_t st) {
+    switch (bn) {
+        case 224: return launch_major<224>(a_k, b_k, ma, mb, mb2, p, st);
+        case 256: return launch_major<256>(a_k, b_k, ma, mb, mb2, p, st);
+        case 128: return launch_major<128>(a_k, b_k, ma, mb, mb2, p, st);
+        default: return launch_major<64>(a_k, b_k, ma, mb, mb2, p, st);
+    }
+}
+
+// x -> TF32 hi (nearest, ties away) and lo = TF32(x - hi), exactly what the splitter warps of gemm3x_kernel compute
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = src[i];
+        const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+        const uint32_t l = (__float_as_uint(x - __uint_as_float(h)) + 0x1000u) & 0xffffe000u;
+        hi[i] = __uint_as_float(h);
+        lo[i] = __uint_as_float(l);
+    }
 }
 
 }  // namespace gemm
@@ -636,9 +666,16 @@ extern "C" int spair_gemm_splits(int M, int N, int K) {
     return (int)(s < 1 ? 1 : s);
 }
 
+extern "C" int spair_split_tf32(const float* src, float* hi, float* lo, int n, void* stream) {
+    SPAIR_REQUIRE(src && hi && lo && n > 0);
+    const int grid = (int)((n + 255) / 256 < 4 * kSMs ? (n + 255) / 256 : 4 * kSMs);
+    gemm::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n);
+    SPAIR_LAUNCH_CHECK();
+}
+
 extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M,
                             int N, int K, const float* bias, int epilogue, int period, float s_colour, float s_alpha, float b_alpha,
-                            float* workspace, int splits, unsigned* kink_ws, int kink_cap, void* stream) {
+                            float* workspace, int splits, unsigned* kink_ws, int kink_cap, const float* B_hi, const float* B_lo, void* stream) {
     SPAIR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1);
     SPAIR_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0);                                   // TMA: 16-byte row pitch
     SPAIR_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0);
@@ -646,11 +683,16 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
     SPAIR_REQUIRE(epilogue != SPAIR_GEMM_EPI_TEXEL || period >= 2);
     SPAIR_REQUIRE(splits == 1 || (workspace != nullptr && epilogue == SPAIR_GEMM_EPI_NONE));
     const int bn = spair_gemm_block_n(N, b_kmajor);
-    CUtensorMap ma, mb;
+    SPAIR_REQUIRE(((uintptr_t)B_hi & 15) == 0 && ((uintptr_t)B_lo & 15) == 0 && (B_hi == nullptr) == (B_lo == nullptr));
+    CUtensorMap ma, mb, mb2;
+    const float* Bm = B_hi ? B_hi : B;       // B itself stays the fp32 matrix (the exact-ReLU re-evaluation reads it)
     bool ok = a_kmajor ? gemm::make_map(&ma, A, K, M, lda, gemm::BK, gemm::BM, true) : gemm::make_map(&ma, A, M, K, lda, 32, gemm::BK, false);
-    ok = ok && (b_kmajor ? gemm::make_map(&mb, B, K, N, ldb, gemm::BK, bn, true) : gemm::make_map(&mb, B, N, K, ldb, 32, gemm::BK, false));
+    ok = ok && (b_kmajor ? gemm::make_map(&mb, Bm, K, N, ldb, gemm::BK, bn, true) : gemm::make_map(&mb, Bm, N, K, ldb, 32, gemm::BK, false));
+    mb2 = mb;
+    if (B_lo) ok = ok && (b_kmajor ? gemm::make_map(&mb2, B_lo, K, N, ldb, gemm::BK, bn, true) : gemm::make_map(&mb2, B_lo, N, K, ldb, 32, gemm::BK, false));
     SPAIR_REQUIRE(ok);
     gemm::Params p;
+    p.b_presplit = B_lo != nullptr;
     p.M = M; p.N = N; p.K = K;
     // the caller sizes the workspace for `splits`; the k-blocks are dealt out evenly and splits that would be empty are dropped
     const int kb_total = (K + gemm::BK - 1) / gemm::BK;
@@ -679,13 +721,7 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
         cudaError_t e = cudaMemsetAsync(kink_ws, 0, sizeof(unsigned), st);
         if (e != cudaSuccess) return (int)e;
     }
-    int rc;
-    switch (bn) {
-        case 224: rc = gemm::launch_major<224>(a_kmajor, b_kmajor, ma, mb, p, st); break;
-        case 256: rc = gemm::launch_major<256>(a_kmajor, b_kmajor, ma, mb, p, st); break;
-        case 128: rc = gemm::launch_major<128>(a_kmajor, b_kmajor, ma, mb, p, st); break;
-        default: rc = gemm::launch_major<64>(a_kmajor, b_kmajor, ma, mb, p, st); break;
-    }
+    int rc = gemm::launch_bn(bn, a_kmajor, b_kmajor, ma, mb, mb2, p, st);
     if (rc == 0 && fixup) {
         gemm::relu_fixup_kernel<<<2 * kSMs, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, N, K, kink_ws, kink_cap);
         SPAIR_LAUNCH_CHECK();
@@ -702,7 +738,7 @@ extern "C" int spair_gemm3x(const float* A, int lda, int a_kmajor, const float* 
 // patches(x)[m][(kh*k + kw)*C + c] = x[b][s*oy + kh][s*ox + kw][c] is read tile by tile with TMA im2col loads.
 extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int k, int stride, int mode, const float* other,
                                  int ld_other, float* out, int ldc, int Cout, const float* bias, int epilogue, float* workspace,
-                                 int splits, unsigned* kink_ws, int kink_cap, void* stream) {
+                                 int splits, unsigned* kink_ws, int kink_cap, const float* w_hi, const float* w_lo, void* stream) {
     SPAIR_REQUIRE(x && other && out && B > 0 && H >= k && W >= k && C > 0 && (C & 31) == 0 && k > 0 && k <= 8 && stride > 0 && stride <= 8);
     SPAIR_REQUIRE((mode == 1 || mode == 2) && Cout > 0 && splits >= 1 && (ld_other & 3) == 0);
     SPAIR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)other & 15) == 0);
@@ -711,22 +747,31 @@ extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int
     SPAIR_REQUIRE(pixels < (1ll << 31));
     const int KK = k * k * C;
     gemm::Params p;
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mb2;
     int bn;
     bool ok;
+    p.b_presplit = 0;
     if (mode == 1) {
         SPAIR_REQUIRE(epilogue == SPAIR_GEMM_EPI_NONE || epilogue == SPAIR_GEMM_EPI_RELU);
-        SPAIR_REQUIRE(splits == 1);
+        SPAIR_REQUIRE(splits == 1 && ((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0 && (w_hi == nullptr) == (w_lo == nullptr));
         p.M = (int)pixels; p.N = Cout; p.K = KK;
         bn = spair_gemm_block_n(p.N, 1);
-        ok = gemm::make_im2col_map(&ma, x, B, H, W, C, k, stride, gemm::BM, true) && gemm::make_map(&mb, other, KK, Cout, ld_other, gemm::BK, bn, true);
+        // w_hi / w_lo: the TF32 planes of the weights (spair_split_tf32); `other` stays the fp32 matrix for the exact-ReLU pass
+        ok = gemm::make_im2col_map(&ma, x, B, H, W, C, k, stride, gemm::BM, true) &&
+             gemm::make_map(&mb, w_hi ? w_hi : other, KK, Cout, ld_other, gemm::BK, bn, true);
+        if (w_lo) {
+            ok = ok && gemm::make_map(&mb2, w_lo, KK, Cout, ld_other, gemm::BK, bn, true);
+            p.b_presplit = 1;
+        }
     } else {
+        SPAIR_REQUIRE(w_hi == nullptr && w_lo == nullptr);
         SPAIR_REQUIRE(epilogue == SPAIR_GEMM_EPI_NONE && bias == nullptr && (splits == 1 || workspace != nullptr));
         p.M = Cout; p.N = KK; p.K = (int)pixels;
         bn = spair_gemm_block_n(p.N, 0);
         ok = gemm::make_map(&ma, other, Cout, (int)pixels, ld_other, 32, gemm::BK, false) && gemm::make_im2col_map(&mb, x, B, H, W, C, k, stride, 32, false);
     }
     SPAIR_REQUIRE(ok);
+    if (!p.b_presplit) mb2 = mb;
     const int kb_total = (p.K + gemm::BK - 1) / gemm::BK;
     const int kb_per = (kb_total + splits - 1) / splits;
     splits = (kb_total + kb_per - 1) / kb_per;
@@ -751,13 +796,7 @@ extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int
         cudaError_t e = cudaMemsetAsync(kink_ws, 0, sizeof(unsigned), st);
         if (e != cudaSuccess) return (int)e;
     }
-    int rc;
-    switch (bn) {
-        case 224: rc = gemm::launch_major<224>(a_k, b_k, ma, mb, p, st); break;
-        case 256: rc = gemm::launch_major<256>(a_k, b_k, ma, mb, p, st); break;
-        case 128: rc = gemm::launch_major<128>(a_k, b_k, ma, mb, p, st); break;
-        default: rc = gemm::launch_major<64>(a_k, b_k, ma, mb, p, st); break;
-    }
+    int rc = gemm::launch_bn(bn, a_k, b_k, ma, mb, mb2, p, st);
     if (rc == 0 && fixup) {
         gemm::relu_fixup_conv_kernel<<<2 * kSMs, 256, 0, st>>>(x, H, W, C, k, stride, Ho, Wo, other, ld_other, bias, out, ldc, Cout, kink_ws, kink_cap);
         SPAIR_LAUNCH_CHECK();
@@ -774,9 +813,10 @@ extern "C" int spair_conv_gemm3x(const float* x, int B, int H, int W, int C, int
 //   dy [B,Ho,Wo,Cout] channels-last (Cout % 32 == 0);  wc: s*s packed class weights [Cin][(a', a, co) = T*T*Cout] with
 //   wc[cls = py*s+px][c][((T-1-a)*T + (T-1-a'))*Cout + co] = w[co][c][py + s*a][px + s*a'];  dx [B,H,W,Cin] (fully overwritten).
 extern "C" int spair_conv_dgrad3x(const float* dy, int B, int H, int W, int Cin, int k, int stride, int Cout, const float* wc,
-                                  float* dx, void* stream) {
+                                  float* dx, const float* wc_hi, const float* wc_lo, void* stream) {
     SPAIR_REQUIRE(dy && wc && dx && B > 0 && H >= k && W >= k && Cin > 0 && Cout > 0 && (Cout & 31) == 0 && k > 0 && stride > 0);
     SPAIR_REQUIRE(k % stride == 0 && k / stride <= 8 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)wc & 15) == 0);
+    SPAIR_REQUIRE(((uintptr_t)wc_hi & 15) == 0 && ((uintptr_t)wc_lo & 15) == 0 && (wc_hi == nullptr) == (wc_lo == nullptr));
     const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1, T = k / stride, KK = T * T * Cout;
     // rows / columns of x beyond the last window receive no gradient: the caller gets zeros there from the class loop below
     // only if every pixel belongs to some class row, i.e. Hp covers all of H
@@ -794,20 +834,17 @@ extern "C" int spair_conv_dgrad3x(const float* dy, int B, int H, int W, int Cin,
             p.conv = 1; p.cv_Ho = Hp; p.cv_Wo = Wp; p.cv_k = T; p.cv_s = 1; p.cv_cpb = Cout / 32; p.cv_base = -(T - 1);
             p.om_s = stride; p.om_H = H; p.om_W = W; p.om_py = py; p.om_px = px;
             p.acc_split = 1; p.kink_ws = nullptr; p.kink_cap = 0;
+            p.b_presplit = wc_lo != nullptr;      // wc_hi / wc_lo: the TF32 planes of the class weights (spair_split_tf32)
             const char* dbg = getenv("SPAIR_GEMM_DEBUG");
             p.debug = dbg ? atoi(dbg) : 0;
-            CUtensorMap ma, mb;
+            CUtensorMap ma, mb, mb2;
             // base positions of the T-wide window over dy: [-(T-1), Wp - (T-1)) -> upper corner = Wp - Wo - (T-1)
             bool ok = gemm::make_im2col_map(&ma, dy, B, Ho, Wo, Cout, T, 1, gemm::BM, true, -(T - 1), -(T - 1), Wp - Wo - (T - 1), Hp - Ho - (T - 1));
-            ok = ok && gemm::make_map(&mb, wc + (size_t)(py * stride + px) * Cin * KK, KK, Cin, KK, gemm::BK, bn, true);
+            ok = ok && gemm::make_map(&mb, (wc_hi ? wc_hi : wc) + (size_t)(py * stride + px) * Cin * KK, KK, Cin, KK, gemm::BK, bn, true);
+            mb2 = mb;
+            if (wc_lo) ok = ok && gemm::make_map(&mb2, wc_lo + (size_t)(py * stride + px) * Cin * KK, KK, Cin, KK, gemm::BK, bn, true);
             SPAIR_REQUIRE(ok);
-            int rc;
-            switch (bn) {
-                case 224: rc = gemm::launch_major<224>(true, true, ma, mb, p, st); break;
-                case 256: rc = gemm::launch_major<256>(true, true, ma, mb, p, st); break;
-                case 128: rc = gemm::launch_major<128>(true, true, ma, mb, p, st); break;
-                default: rc = gemm::launch_major<64>(true, true, ma, mb, p, st); break;
-            }
+            const int rc = gemm::launch_bn(bn, true, true, ma, mb, mb2, p, st);
             if (rc != 0) return rc;
         }
     return 0;

@@ -88,9 +88,10 @@ _SIGNATURES = {
     "spair_broadcast_rows": [_P, _I, _I, _P, _P],
     "spair_gemm_block_n": [_I, _I],
     "spair_gemm_splits": [_I, _I, _I],
-    "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P],
-    "spair_conv_gemm3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P],
-    "spair_conv_dgrad3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spair_gemm3x": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _I, _P, _I, _P, _P, _P],
+    "spair_split_tf32": [_P, _P, _P, _I, _P],
+    "spair_conv_gemm3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P],
+    "spair_conv_dgrad3x": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "spair_im2col_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_col2im_nhwc": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spair_transpose_batched": [_P, _I, _I, _I, _P, _P],
@@ -111,7 +112,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 RENDER_MAX_TEXELS, RENDER_MAX_CHANNELS = 1024, 4   # spair_render_fwd/bwd: G*G <= 1024, C <= 4 (csrc/render.cu)
 NUM_SMS = 148          # kSMs of csrc/common.cuh (B200: 2 dies x 74 SMs)
 MAX_NEIGHBOURS = 12   # SPAIR_MAX_NEIGHBOURS of include/spair_b200.h (N_LOOKBACK <= 2)
-ABI_VERSION = 4       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
+ABI_VERSION = 5       # SPAIR_ABI_VERSION of include/spair_b200.h this binding was written against
 
 
 def lib() -> ctypes.CDLL:
@@ -404,11 +405,31 @@ def _kink_workspace(device):
     return ws
 
 
+class SplitWeight:
+    """A weight matrix with its TF32 hi / lo planes (``spair_split_tf32``), made once per step: the GEMM kernels then load the
+    planes of their B operand instead of splitting every tile of it (half of the splitter work, identical results).
+    ``w`` is the fp32 matrix itself (a view is fine as long as hi / lo are asked for the same view)."""
+
+    def __init__(self, w):
+        self.w = _contig(w.detach(), "weight")
+        planes = torch.empty((2,) + tuple(self.w.shape), device=self.w.device, dtype=torch.float32)
+        self.hi, self.lo = planes[0], planes[1]
+        with torch.cuda.device(self.w.device):
+            _check(lib().spair_split_tf32(_ptr(self.w), _ptr(self.hi), _ptr(self.lo), self.w.numel(), _stream()), "spair_split_tf32")
+
+    @property
+    def shape(self):
+        return self.w.shape
+
+
 def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, period=2, scales=(1.0, 1.0, 0.0), splits=None,
            exact_relu=True):
     """out[M,N] = op(A) . op(B) (+ bias) on the tensor cores at fp32 accuracy (see spair_gemm3x in include/spair_b200.h).
-    a_kmajor: A is [M,K] (else [K,M]); b_kmajor: B is [N,K] (else [K,N]).  ``exact_relu``: with the ReLU epilogue, outputs
-    within rounding error of the kink are re-evaluated in float64 (two launches instead of one)."""
+    a_kmajor: A is [M,K] (else [K,M]); b_kmajor: B is [N,K] (else [K,N]); B may be a ``SplitWeight``.  ``exact_relu``: with
+    the ReLU epilogue, outputs within rounding error of the kink are re-evaluated in float64 (two launches instead of one)."""
+    B_hi = B_lo = None
+    if isinstance(B, SplitWeight):
+        B, B_hi, B_lo = B.w, B.hi, B.lo
     M, N = out.shape
     Kd = A.shape[1] if a_kmajor else A.shape[0]
     assert (A.shape[0] if a_kmajor else A.shape[1]) == M and (B.shape[0] if b_kmajor else B.shape[1]) == N
@@ -420,7 +441,8 @@ def gemm3x(A, a_kmajor, B, b_kmajor, out, bias=None, epilogue=GEMM_EPI_NONE, per
     kink = _kink_workspace(out.device) if fix else None
     _check(lib().spair_gemm3x(_ptr(A), _ld(A), int(a_kmajor), _ptr(B), _ld(B), int(b_kmajor), _ptr(out), _ld(out), M, N, Kd,
                               _ptr(bias), epilogue, period, float(scales[0]), float(scales[1]), float(scales[2]), _ptr(ws),
-                              splits, kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _stream()), "spair_gemm3x")
+                              splits, kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _ptr(B_hi), _ptr(B_lo), _stream()),
+           "spair_gemm3x")
     if splits > 1 or fix:
         global LAUNCH_COUNT
         LAUNCH_COUNT += 1      # the fixed-order split-K reduction / the ReLU sign fix-up
@@ -457,11 +479,15 @@ def conv_supported(x, k: int, stride: int) -> bool:
 def conv_fwd(x, k: int, stride: int, wr, bias, out, relu: bool, exact_relu=True):
     """out[B*Ho*Wo, Cout] = act(patches(x) . wr^T + bias): x [B,H,W,C] channels-last, wr [Cout, k*k*C] in (kh, kw, c) order."""
     B, H, W, C = x.shape
+    w_hi = w_lo = None
+    if isinstance(wr, SplitWeight):
+        wr, w_hi, w_lo = wr.w, wr.hi, wr.lo
     fix = relu and exact_relu and out.numel() < (1 << 32)
     kink = _kink_workspace(out.device) if fix else None
     _check(lib().spair_conv_gemm3x(_ptr(_contig(x, "x")), B, H, W, C, k, stride, 1, _ptr(wr), _ld(wr), _ptr(out), _ld(out),
                                    wr.shape[0], _ptr(bias), GEMM_EPI_RELU if relu else GEMM_EPI_NONE, None, 1,
-                                   kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _stream()), "spair_conv_gemm3x")
+                                   kink.data_ptr() if fix else None, KINK_CAP if fix else 0, _ptr(w_hi), _ptr(w_lo), _stream()),
+           "spair_conv_gemm3x")
     if fix:
         global LAUNCH_COUNT
         LAUNCH_COUNT += 1
@@ -474,7 +500,7 @@ def conv_wgrad(x, k: int, stride: int, dy, d_wr):
     splits = lib().spair_gemm_splits(Cout, KK, dy.shape[0])
     ws = _gemm_workspace(d_wr.device, splits * Cout * KK) if splits > 1 else None
     _check(lib().spair_conv_gemm3x(_ptr(_contig(x, "x")), B, H, W, C, k, stride, 2, _ptr(dy), _ld(dy), _ptr(d_wr), _ld(d_wr),
-                                   Cout, None, GEMM_EPI_NONE, _ptr(ws), splits, None, 0, _stream()), "spair_conv_gemm3x")
+                                   Cout, None, GEMM_EPI_NONE, _ptr(ws), splits, None, 0, None, None, _stream()), "spair_conv_gemm3x")
     if splits > 1:
         global LAUNCH_COUNT
         LAUNCH_COUNT += 1
@@ -501,8 +527,11 @@ def conv_dgrad(dy, B: int, k: int, stride: int, wc, dx):
     _, H, W, Cin = dx.shape
     Cout = dy.shape[1]
     n_cls = stride * stride
+    wc_hi = wc_lo = None
+    if isinstance(wc, SplitWeight):
+        wc, wc_hi, wc_lo = wc.w, wc.hi, wc.lo
     _check(lib().spair_conv_dgrad3x(_ptr(_contig(dy, "dy")), B, H, W, Cin, k, stride, Cout, _ptr(_contig(wc, "wc")),
-                                    _ptr(_contig(dx, "dx")), _stream()), "spair_conv_dgrad3x")
+                                    _ptr(_contig(dx, "dx")), _ptr(wc_hi), _ptr(wc_lo), _stream()), "spair_conv_dgrad3x")
     global LAUNCH_COUNT
     LAUNCH_COUNT += n_cls - 1
 

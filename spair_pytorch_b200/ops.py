@@ -337,16 +337,21 @@ class DecoderFunction(torch.autograd.Function):
         w0_p.copy_(w0)
         h0 = torch.empty(n, w0.shape[0], device=dev, dtype=torch.float32)
         K.gemm3x(attr_p, True, w0_p, True, h0, b0, epilogue=K.GEMM_EPI_RELU)
+        # the two wide weights are split into their TF32 hi / lo planes once (one small launch each) and serve the forward
+        # and the input-gradient GEMM: the kernels then only split the activation tiles
+        w1s, w2s = K.SplitWeight(w1), K.SplitWeight(w2)
         h1 = torch.empty(n, w1.shape[0], device=dev, dtype=torch.float32)
-        K.gemm3x(h0, True, w1, True, h1, b1, epilogue=K.GEMM_EPI_RELU)
+        K.gemm3x(h0, True, w1s, True, h1, b1, epilogue=K.GEMM_EPI_RELU)
         texels = torch.empty(n, w2.shape[0], device=dev, dtype=torch.float32)
-        K.gemm3x(h1, True, w2, True, texels, b2, epilogue=K.GEMM_EPI_TEXEL, period=period, scales=scales)
+        K.gemm3x(h1, True, w2s, True, texels, b2, epilogue=K.GEMM_EPI_TEXEL, period=period, scales=scales)
         ctx.save_for_backward(attr_p, h0, h1, w0_p, w1, w2)
+        ctx.split_weights = (w1s, w2s)
         return texels
 
     @staticmethod
     def backward(ctx, d_logits):
         attr, h0, h1, w0, w1, w2 = ctx.saved_tensors
+        w1s, w2s = ctx.split_weights
         d_logits = _c(d_logits)
         n, dev = attr.shape[0], attr.device
         d_w2 = torch.empty_like(w2)
@@ -354,13 +359,13 @@ class DecoderFunction(torch.autograd.Function):
         d_b2 = torch.empty(w2.shape[0], device=dev, dtype=torch.float32)
         K.relu_bwd_colsum(d_logits, None, d_b2)
         d_h1 = torch.empty_like(h1)
-        K.gemm3x(d_logits, True, w2, False, d_h1)
+        K.gemm3x(d_logits, True, w2s, False, d_h1)
         d_b1 = torch.empty(w1.shape[0], device=dev, dtype=torch.float32)
         K.relu_bwd_colsum(d_h1, h1, d_b1)
         d_w1 = torch.empty_like(w1)
         K.gemm3x(d_h1, False, h0, False, d_w1)
         d_h0 = torch.empty_like(h0)
-        K.gemm3x(d_h1, True, w1, False, d_h0)
+        K.gemm3x(d_h1, True, w1s, False, d_h0)
         d_b0 = torch.empty(w0.shape[0], device=dev, dtype=torch.float32)
         K.relu_bwd_colsum(d_h0, h0, d_b0)
         d_w0 = torch.empty_like(w0)
@@ -437,29 +442,31 @@ class ConvTailFunction(torch.autograd.Function):
         B0, C0, H0, W0 = y0.shape
         x = torch.empty(B0, H0, W0, C0, device=y0.device, dtype=torch.float32)      # channels-last from here on
         K.transpose_batched(y0.contiguous().view(B0, C0, H0 * W0), x.view(B0, H0 * W0, C0))
-        saved, shapes = [], []
+        saved, shapes, split = [], [], []
         for li, (k, s, relu) in enumerate(specs):
             w, b = params[2 * li].detach(), params[2 * li + 1].detach().contiguous()
             Bn, H, W, Cin = x.shape
             Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
             M = Bn * Ho * Wo
             wr = w.permute(0, 2, 3, 1).reshape(w.shape[0], k * k * Cin).contiguous()     # [Cout, (kh, kw, c)]
+            wrs = K.SplitWeight(wr)           # TF32 hi / lo planes, once: forward and (1x1 layers) input gradient
+            split.append(wrs)
             y = torch.empty(M, w.shape[0], device=x.device, dtype=torch.float32)
             if k == 1 and s == 1:
                 a = x.view(M, Cin)
-                K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
+                K.gemm3x(a, True, wrs, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
             elif IMPLICIT_CONV and K.conv_supported(x, k, s):
                 a = x                                   # implicit GEMM: the producer warp reads the patches with TMA im2col
-                K.conv_fwd(x, k, s, wr, b, y, relu)
+                K.conv_fwd(x, k, s, wrs, b, y, relu)
             else:
                 a = torch.empty(M, k * k * Cin, device=x.device, dtype=torch.float32)
                 K.im2col_nhwc(x, k, s, a)
-                K.gemm3x(a, True, wr, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
+                K.gemm3x(a, True, wrs, True, y, b, epilogue=K.GEMM_EPI_RELU if relu else K.GEMM_EPI_NONE)
             saved += [a, wr, y]
             shapes.append((Bn, H, W, Cin, Ho, Wo, tuple(w.shape)))
             x = y.view(Bn, Ho, Wo, w.shape[0])
         ctx.save_for_backward(*saved)
-        ctx.specs, ctx.shapes = specs, shapes
+        ctx.specs, ctx.shapes, ctx.split = specs, shapes, split
         Bn, Ho, Wo, F = x.shape
         feat = torch.empty(Bn, F, Ho, Wo, device=x.device, dtype=torch.float32)
         K.transpose_batched(x.view(Bn, Ho * Wo, F), feat.view(Bn, F, Ho * Wo))
@@ -492,11 +499,11 @@ class ConvTailFunction(torch.autograd.Function):
                 # transposed convolution as s*s implicit GEMMs over dy (no d_col matrix, no scatter pass)
                 w4 = wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2)
                 dx = torch.empty(Bn, H, W, Cin, device=dy.device, dtype=torch.float32)
-                K.conv_dgrad(dy, Bn, k, s, K.pack_dgrad_weights(w4, s), dx)
+                K.conv_dgrad(dy, Bn, k, s, K.SplitWeight(K.pack_dgrad_weights(w4, s)), dx)
                 dy = dx.view(Bn * H * W, Cin)
                 continue
             da = torch.empty(dy.shape[0], wr.shape[1], device=dy.device, dtype=torch.float32)
-            K.gemm3x(dy, True, wr, False, da)
+            K.gemm3x(dy, True, ctx.split[li], False, da)
             if k == 1 and s == 1:
                 dy = da
             else:

@@ -277,3 +277,45 @@ def test_implicit_conv_dgrad_matches_torch(B, H, W, Cin, Cout, k, s):
     scale = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double().abs(), w.double().abs(), stride=s)
     scale = torch.nn.functional.pad(scale, (0, W - scale.shape[3], 0, H - scale.shape[2])).permute(0, 2, 3, 1) + 1e-30
     assert ((dx.double() - ref).abs() / scale.clamp_min(1e-6)).max().item() < 5e-6
+
+
+def test_presplit_weights_give_identical_results():
+    """A weight operand split into its TF32 hi / lo planes ONCE (spair_split_tf32 / kernels.SplitWeight) instead of tile by
+    tile inside the GEMM: bitwise the same results — plain / ReLU (incl. the exact-sign pass, which still reads the fp32
+    weights) / texel epilogues with the weight K-major (y = x W^T), the same planes MN-major (dx = dy W), the implicit-GEMM
+    convolution and its input gradient; ragged N, K tails and a padded class-weight tensor."""
+    k_ = K()
+    g = torch.Generator(device=DEV).manual_seed(77)
+    for M, N, Kd in ((700, 520, 260), (3872, 1568, 256), (257, 100, 36)):
+        x = torch.randn(M, Kd, device=DEV, generator=g)
+        w = torch.randn(N, Kd, device=DEV, generator=g) * 0.2
+        b = torch.randn(N, device=DEV, generator=g)
+        ws = k_.SplitWeight(w)
+        assert torch.equal(ws.hi + ws.lo, w) or float((ws.hi + ws.lo - w).abs().max()) <= 2.0 ** -23 * float(w.abs().max())
+        for kwargs in (dict(), dict(bias=b, epilogue=k_.GEMM_EPI_RELU), dict(bias=b, epilogue=k_.GEMM_EPI_TEXEL, period=2, scales=(2.0, 0.1, 5.0))):
+            y0, y1 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+            k_.gemm3x(x, True, w, True, y0, **kwargs)
+            k_.gemm3x(x, True, ws, True, y1, **kwargs)
+            assert torch.equal(y0, y1), (M, N, Kd, kwargs.get("epilogue"))
+        dy = torch.randn(M, N, device=DEV, generator=g)
+        d0, d1 = torch.empty(M, Kd, device=DEV), torch.empty(M, Kd, device=DEV)
+        k_.gemm3x(dy, True, w, False, d0)
+        k_.gemm3x(dy, True, ws, False, d1)
+        assert torch.equal(d0, d1)
+    for B, H, W, C, Cout, k, s in ((3, 50, 50, 128, 128, 4, 2), (5, 24, 24, 128, 100, 4, 2)):
+        x = torch.randn(B, H, W, C, device=DEV, generator=g)
+        w = torch.randn(Cout, k * k * C, device=DEV, generator=g) * 0.05
+        b = torch.randn(Cout, device=DEV, generator=g)
+        Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+        y0, y1 = torch.empty(B * Ho * Wo, Cout, device=DEV), torch.empty(B * Ho * Wo, Cout, device=DEV)
+        k_.conv_fwd(x, k, s, w, b, y0, relu=True)
+        k_.conv_fwd(x, k, s, k_.SplitWeight(w), b, y1, relu=True)
+        assert torch.equal(y0, y1)
+        if Cout % 32 == 0:
+            w4 = w.view(Cout, k, k, C).permute(0, 3, 1, 2)
+            wc = k_.pack_dgrad_weights(w4, s)
+            dyc = torch.randn(B * Ho * Wo, Cout, device=DEV, generator=g)
+            dx0, dx1 = torch.empty(B, H, W, C, device=DEV), torch.empty(B, H, W, C, device=DEV)
+            k_.conv_dgrad(dyc, B, k, s, wc, dx0)
+            k_.conv_dgrad(dyc, B, k, s, k_.SplitWeight(wc), dx1)
+            assert torch.equal(dx0, dx1)
