@@ -189,17 +189,17 @@ def kernel_roofline(net, x, steps=20):
     pl, pr, pt, pb = net.backbone.padding.padding
     s0 = conv0.stride[0]
     Ho, Wo = (I + pt + pb - 4) // s0 + 1, (I + pl + pr - 4) // s0 + 1
-    stem_y = torch.empty(B, conv0.out_channels, Ho, Wo, device=dev)
+    stem_y = torch.empty(B, Ho, Wo, conv0.out_channels, device=dev)      # channels-last, as the step runs it (GEMM tail)
     stem_dy = torch.randn_like(stem_y)
     stem_ws = K.stem_bwd_workspace(C, conv0.out_channels, dev)
     stem_dw, stem_db = torch.empty_like(conv0.weight), torch.empty_like(conv0.bias)
     w0, b0 = conv0.weight.detach().contiguous(), conv0.bias.detach().contiguous()
 
     def t_stem_fwd():
-        K.stem_conv_fwd(x, w0, b0, s0, pt, pl, Ho, Wo, stem_y)
+        K.stem_conv_fwd(x, w0, b0, s0, pt, pl, Ho, Wo, stem_y, True)
 
     def t_stem_bwd():
-        K.stem_conv_bwd(x, stem_y, stem_dy, tuple(w0.shape), s0, pt, pl, stem_ws, stem_dw, stem_db)
+        K.stem_conv_bwd(x, stem_y, stem_dy, tuple(w0.shape), s0, pt, pl, stem_ws, stem_dw, stem_db, True)
 
     # algorithmic bytes per image
     per_image = {

@@ -374,14 +374,16 @@ int spair_sweep_bwd_tc(const spair_sweep_dims* dims, const int* order, const int
  * the backward reads dy and the saved post-ReLU y once and produces d_w [Cout,C,4,4] and d_bias [Cout]
  * (the image has no gradient).  Supported: C in {1,3}, Cout = 128, k = 4; padding is the ZeroPad2d's
  * (top, left) — right / bottom padding is implied by Ho, Wo.  ws: workspace of
- * spair_stem_bwd_ctas() * Cout * (C*16 + 4) floats, 16-byte aligned.
+ * spair_stem_bwd_ctas() * Cout * (C*16 + 4) floats, 16-byte aligned.  nhwc = 1: y and dy are channels-last
+ * [B,Ho,Wo,Cout] (16-byte aligned) — the layout the GEMM tail of the backbone (spair_conv_gemm3x) consumes, so no
+ * transpose pass separates the two; same values either way.
  * ---------------------------------------------------------------------------------- */
 int spair_stem_bwd_ctas(void);
 int spair_stem_conv_fwd(const float* x, const float* w, const float* bias, int B, int C, int Ih, int Iw, int Cout,
-                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* y, void* stream);
+                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int nhwc, float* y, void* stream);
 int spair_stem_conv_bwd(const float* x, const float* y, const float* dy, int B, int C, int Ih, int Iw, int Cout,
-                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* ws, float* d_w, float* d_bias,
-                        void* stream);
+                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int nhwc, float* ws, float* d_w,
+                        float* d_bias, void* stream);
 
 /* out[r][:] = row[:] for r < rows (vectorised when cols % 4 == 0): pre-fills the decoder's [B*HW, G*G*(C+1)] logits
  * (reference models.py:165,477) with the bias so that the output GEMM runs with beta = 1. */

@@ -9,7 +9,9 @@
 // gradient in the model, so no dgrad exists.
 //
 // forward : thread = PP output pixels x all output channels; the C*16 input taps of a pixel live in registers and are
-//           reused for every channel, weights / bias are 128-bit shared-memory broadcasts, stores are coalesced rows.
+//           reused for every channel, weights / bias are 128-bit shared-memory broadcasts, stores are coalesced rows
+//           (NCHW) or, for the GEMM tail that consumes the map channels-last, eight channels = one 32-byte sector per
+//           pixel and store pair (NHWC: no transpose pass between the stem and conv_1, either way).
 // backward: dW[o][t] = sum_{b,p} g[b,o,p] * tap[b,p,t], g = dY * (Y > 0), is a [128 x P] x [P x (T+1)] contraction with
 //           P = B*Ho*Wo (640 k) — persistent CTAs walk 64-pixel segments, stage g (transposed) and the taps (plus a
 //           ones column that yields db) in shared memory, and keep a 4 x 4 register tile per thread; per-CTA partials
@@ -22,13 +24,14 @@ constexpr int kStemK = 4;                 // kernel side
 constexpr int kStemCout = 128;
 constexpr int kStemFwdThreads = 128;
 constexpr int kStemSeg = 64;              // pixels per backward segment
-constexpr int kStemGPitch = kStemCout + 1;   // transposed gradient tile pitch: conflict-free for consecutive pixels
+constexpr int kStemGPitch = kStemCout + 4;   // [pixel][channel] gradient tile pitch: 16-byte aligned rows (NHWC staging stores
+                                             // 128 bits), conflict-free column writes for consecutive pixels (NCHW staging)
 
 struct StemArgs {
     const float* x;      // [B,C,Ih,Iw]
     const float* w;      // [Cout,C,4,4]
     const float* bias;   // [Cout]
-    float* y;            // [B,Cout,Ho,Wo] post-ReLU
+    float* y;            // [B,Cout,Ho,Wo] post-ReLU (NHWC variant: [B,Ho,Wo,Cout])
     int B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l;
 };
 
@@ -49,7 +52,7 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ xb, int Ih, 
         }
 }
 
-template <int C, int PP>
+template <int C, int PP, bool NHWC>
 __global__ void __launch_bounds__(kStemFwdThreads) stem_fwd_kernel(StemArgs p) {
     constexpr int T = C * 16;
     __shared__ __align__(16) float w_s[kStemCout * T];
@@ -71,6 +74,39 @@ __global__ void __launch_bounds__(kStemFwdThreads) stem_fwd_kernel(StemArgs p) {
     }
     __syncthreads();
     float* yb = p.y + (size_t)b * kStemCout * npix;
+    if constexpr (NHWC) {
+        // eight output channels per pass: a pixel's eight values are one 32-byte sector, written by two 128-bit stores of
+        // the same thread (same FMA order per output as the NCHW variant: bitwise the same values)
+#pragma unroll 1
+        for (int o = 0; o < kStemCout; o += 8) {
+            float acc[PP][8];
+#pragma unroll
+            for (int j = 0; j < PP; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][i] = b_s[o + i];
+#pragma unroll
+            for (int t4 = 0; t4 < T / 4; ++t4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w = *reinterpret_cast<const float4*>(w_s + (o + i) * T + 4 * t4);
+#pragma unroll
+                    for (int j = 0; j < PP; ++j) {
+                        acc[j][i] = fmaf(w.x, tap[j][4 * t4 + 0], acc[j][i]);
+                        acc[j][i] = fmaf(w.y, tap[j][4 * t4 + 1], acc[j][i]);
+                        acc[j][i] = fmaf(w.z, tap[j][4 * t4 + 2], acc[j][i]);
+                        acc[j][i] = fmaf(w.w, tap[j][4 * t4 + 3], acc[j][i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PP; ++j)
+                if (valid[j]) {
+                    float4* dst = reinterpret_cast<float4*>(yb + (size_t)(pix0 + j * kStemFwdThreads) * kStemCout + o);
+                    dst[0] = make_float4(fmaxf(acc[j][0], 0.0f), fmaxf(acc[j][1], 0.0f), fmaxf(acc[j][2], 0.0f), fmaxf(acc[j][3], 0.0f));
+                    dst[1] = make_float4(fmaxf(acc[j][4], 0.0f), fmaxf(acc[j][5], 0.0f), fmaxf(acc[j][6], 0.0f), fmaxf(acc[j][7], 0.0f));
+                }
+        }
+    } else {
 #pragma unroll 2
     for (int o = 0; o < kStemCout; ++o) {
         float acc[PP];
@@ -91,6 +127,7 @@ __global__ void __launch_bounds__(kStemFwdThreads) stem_fwd_kernel(StemArgs p) {
         for (int j = 0; j < PP; ++j)
             if (valid[j]) yb[(size_t)o * npix + pix0 + j * kStemFwdThreads] = fmaxf(acc[j], 0.0f);
     }
+    }
 }
 
 struct StemBwdArgs {
@@ -100,13 +137,14 @@ struct StemBwdArgs {
     float* ws;           // [Cout * TP][gridDim.x] per-CTA partial sums (CTA index fastest: the reduction reads rows)
     int B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l, n_seg_per_image;
     int vec_ok;          // rows of y / dy are 16-byte aligned: 128-bit staging loads
+    int nhwc;            // y / dy are [B,Ho,Wo,Cout]: a segment is one contiguous 64 x 512-byte block
 };
 
 // TP = padded tap count incl. the ones column (multiple of 4); threads = 32 * TP / 4
 template <int C>
 __global__ void __launch_bounds__(32 * (C * 16 + 4) / 4) stem_bwd_kernel(StemBwdArgs p) {
     constexpr int T = C * 16, TP = T + 4, TG = TP / 4, NT = 32 * TG;
-    __shared__ float g_s[kStemSeg * kStemGPitch];
+    __shared__ __align__(16) float g_s[kStemSeg * kStemGPitch];
     __shared__ __align__(16) float in_s[kStemSeg * TP];
     const int og = threadIdx.x & 31, tg = threadIdx.x >> 5;
     const int npix = p.Ho * p.Wo;
@@ -141,7 +179,25 @@ __global__ void __launch_bounds__(32 * (C * 16 + 4) / 4) stem_bwd_kernel(StemBwd
         // masked gradient, transposed to [pixel][channel]; 128-bit streaming loads along the pixels when rows allow it
         const float* yb = p.y + (size_t)b * kStemCout * npix;
         const float* dyb = p.dy + (size_t)b * kStemCout * npix;
-        if (p.vec_ok) {
+        if (p.nhwc) {
+            // channels-last: the segment's 64 pixels x 128 channels are contiguous in memory and already [pixel][channel]
+            constexpr int O4 = kStemCout / 4;
+#pragma unroll 4
+            for (int idx = threadIdx.x; idx < kStemSeg * O4; idx += NT) {
+                const int pl = idx / O4, o4 = idx - pl * O4;
+                float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (pix0 + pl < npix) {
+                    const size_t a = ((size_t)pix0 + pl) * kStemCout + 4 * o4;
+                    const float4 yv = __ldcs(reinterpret_cast<const float4*>(yb + a));
+                    const float4 dv = __ldcs(reinterpret_cast<const float4*>(dyb + a));
+                    g.x = yv.x > 0.0f ? dv.x : 0.0f;
+                    g.y = yv.y > 0.0f ? dv.y : 0.0f;
+                    g.z = yv.z > 0.0f ? dv.z : 0.0f;
+                    g.w = yv.w > 0.0f ? dv.w : 0.0f;
+                }
+                *reinterpret_cast<float4*>(g_s + pl * kStemGPitch + 4 * o4) = g;
+            }
+        } else if (p.vec_ok) {
             constexpr int Q = kStemSeg / 4;
 #pragma unroll 4
             for (int idx = threadIdx.x; idx < kStemCout * Q; idx += NT) {
@@ -240,31 +296,34 @@ static bool stem_shape_ok(int B, int C, int Ih, int Iw, int Cout, int k, int str
 extern "C" int spair_stem_bwd_ctas(void) { return kSMs * 4; }
 
 extern "C" int spair_stem_conv_fwd(const float* x, const float* w, const float* bias, int B, int C, int Ih, int Iw, int Cout,
-                                   int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* y, void* stream) {
-    SPAIR_REQUIRE(x && w && bias && y);
+                                   int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int nhwc, float* y, void* stream) {
+    SPAIR_REQUIRE(x && w && bias && y && (!nhwc || ((uintptr_t)y % 16) == 0));
     SPAIR_REQUIRE(stem_shape_ok(B, C, Ih, Iw, Cout, k, stride, pad_t, pad_l, Ho, Wo));
     StemArgs a{x, w, bias, y, B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l};
     const int npix = Ho * Wo;
     if (C == 1) {
         dim3 grid((npix + kStemFwdThreads * 4 - 1) / (kStemFwdThreads * 4), B);
-        stem_fwd_kernel<1, 4><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
+        if (nhwc) stem_fwd_kernel<1, 4, true><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
+        else stem_fwd_kernel<1, 4, false><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
     } else {
         dim3 grid((npix + kStemFwdThreads - 1) / kStemFwdThreads, B);
-        stem_fwd_kernel<3, 1><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
+        if (nhwc) stem_fwd_kernel<3, 1, true><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
+        else stem_fwd_kernel<3, 1, false><<<grid, kStemFwdThreads, 0, (cudaStream_t)stream>>>(a);
     }
     SPAIR_LAUNCH_CHECK();
 }
 
 extern "C" int spair_stem_conv_bwd(const float* x, const float* y, const float* dy, int B, int C, int Ih, int Iw, int Cout,
-                                   int k, int stride, int pad_t, int pad_l, int Ho, int Wo, float* ws, float* d_w,
+                                   int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int nhwc, float* ws, float* d_w,
                                    float* d_bias, void* stream) {
     SPAIR_REQUIRE(x && y && dy && ws && d_w && d_bias && ((uintptr_t)ws % 16) == 0);
+    SPAIR_REQUIRE(!nhwc || (((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0));
     SPAIR_REQUIRE(stem_shape_ok(B, C, Ih, Iw, Cout, k, stride, pad_t, pad_l, Ho, Wo));
     const int n_seg_per_image = (Ho * Wo + kStemSeg - 1) / kStemSeg;
     const long long n_seg = (long long)B * n_seg_per_image;
     const int n_cta = (int)(n_seg < spair_stem_bwd_ctas() ? n_seg : spair_stem_bwd_ctas());
     const int vec_ok = ((Ho * Wo) % 4 == 0) && ((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0;
-    StemBwdArgs a{x, y, dy, ws, B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l, n_seg_per_image, vec_ok};
+    StemBwdArgs a{x, y, dy, ws, B, Ih, Iw, Ho, Wo, stride, pad_t, pad_l, n_seg_per_image, vec_ok, nhwc};
     const int T = C * 16, TP = T + 4;
     if (C == 1) stem_bwd_kernel<1><<<n_cta, 32 * (16 + 4) / 4, 0, (cudaStream_t)stream>>>(a);
     else stem_bwd_kernel<3><<<n_cta, 32 * (48 + 4) / 4, 0, (cudaStream_t)stream>>>(a);

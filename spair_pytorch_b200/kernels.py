@@ -83,8 +83,8 @@ _SIGNATURES = {
     "spair_kl_bwd": [_P] * 8 + [_I, _I, _I, _P, _P, _P, _P],
     "spair_relu_bwd": [_P, _I, _P, _I, _I, _I, _P],
     "spair_stem_bwd_ctas": [],
-    "spair_stem_conv_fwd": [_P, _P, _P] + [_I] * 11 + [_P, _P],
-    "spair_stem_conv_bwd": [_P, _P, _P] + [_I] * 11 + [_P, _P, _P, _P],
+    "spair_stem_conv_fwd": [_P, _P, _P] + [_I] * 12 + [_P, _P],
+    "spair_stem_conv_bwd": [_P, _P, _P] + [_I] * 12 + [_P, _P, _P, _P],
     "spair_broadcast_rows": [_P, _I, _I, _P, _P],
     "spair_gemm_block_n": [_I, _I],
     "spair_gemm_splits": [_I, _I, _I],
@@ -343,12 +343,13 @@ def stem_supported(C: int, Cout: int, k) -> bool:
     return C in (1, 3) and Cout == 128 and tuple(k) == (4, 4)
 
 
-def stem_conv_fwd(x, w, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int, y):
+def stem_conv_fwd(x, w, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int, y, channels_last=False):
+    """y [B,Cout,Ho,Wo], or [B,Ho,Wo,Cout] with ``channels_last``."""
     B, C, Ih, Iw = x.shape
     for t in (x, w, bias, y):
         _contig(t, "stem tensor")
     _check(lib().spair_stem_conv_fwd(_ptr(x), _ptr(w), _ptr(bias), B, C, Ih, Iw, w.shape[0], w.shape[2], stride, pad_t, pad_l,
-                                     Ho, Wo, _ptr(y), _stream()), "spair_stem_conv_fwd")
+                                     Ho, Wo, int(channels_last), _ptr(y), _stream()), "spair_stem_conv_fwd")
 
 
 def broadcast_rows(row, rows: int, out):
@@ -360,13 +361,13 @@ def stem_bwd_workspace(C: int, Cout: int, device) -> torch.Tensor:
     return torch.empty(lib().spair_stem_bwd_ctas() * Cout * (C * 16 + 4), device=device, dtype=torch.float32)
 
 
-def stem_conv_bwd(x, y, dy, w_shape, stride: int, pad_t: int, pad_l: int, ws, d_w, d_bias):
+def stem_conv_bwd(x, y, dy, w_shape, stride: int, pad_t: int, pad_l: int, ws, d_w, d_bias, channels_last=False):
     B, C, Ih, Iw = x.shape
-    Ho, Wo = y.shape[2], y.shape[3]
+    Ho, Wo = (y.shape[1], y.shape[2]) if channels_last else (y.shape[2], y.shape[3])
     for t in (x, y, dy, ws, d_w, d_bias):
         _contig(t, "stem tensor")
     _check(lib().spair_stem_conv_bwd(_ptr(x), _ptr(y), _ptr(dy), B, C, Ih, Iw, w_shape[0], w_shape[2], stride, pad_t, pad_l,
-                                     Ho, Wo, _ptr(ws), _ptr(d_w), _ptr(d_bias), _stream()), "spair_stem_conv_bwd")
+                                     Ho, Wo, int(channels_last), _ptr(ws), _ptr(d_w), _ptr(d_bias), _stream()), "spair_stem_conv_bwd")
 
 
 # ----------------------------------------------------------------------------------------

@@ -83,9 +83,10 @@ class Backbone(Module):
         with torch.no_grad():
             return self(probe.to(next(self.parameters()).device)).shape[1:]
 
-    def _fused_stem(self, x):
+    def _fused_stem(self, x, channels_last=False):
         """ZeroPad2d + conv_0 + act_0 as one sm_100a kernel each way (csrc/stem.cu) when the layer has the shape the
-        kernel covers and the image needs no gradient; None otherwise (library path)."""
+        kernel covers and the image needs no gradient; None otherwise (library path).  ``channels_last``: the map is
+        written [B,Ho,Wo,Cout], the layout the GEMM tail consumes."""
         conv = self.net[0]
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and not x.requires_grad
                 and isinstance(conv, Conv2d) and isinstance(self.net[1], ReLU) and conv.bias is not None
@@ -101,16 +102,16 @@ class Backbone(Module):
         Wo = (x.shape[3] + pl + pr - k) // stride + 1
         if Ho <= 0 or Wo <= 0:
             return None
-        return ops.StemConvFunction.apply(x, conv.weight, conv.bias, stride, pt, pl, Ho, Wo)
+        return ops.StemConvFunction.apply(x, conv.weight, conv.bias, stride, pt, pl, Ho, Wo, channels_last)
 
-    def _gemm_tail(self, y):
-        """conv_1 .. conv_out on the tcgen05 GEMM (ops.ConvTailFunction) when every layer has the shape it covers;
-        None otherwise (cuDNN)."""
+    def _gemm_tail_plan(self, x):
+        """(specs, params) of conv_1 .. conv_out for the tcgen05 GEMM path (ops.ConvTailFunction) when every layer has the
+        shape it covers; None otherwise (cuDNN)."""
         from . import ops
         layers = list(self.net)[2:]
-        if not (ops.USE_TENSOR_CORE_GEMM and y.is_cuda and y.dtype == torch.float32):
+        if not (ops.USE_TENSOR_CORE_GEMM and x.is_cuda and x.dtype == torch.float32 and isinstance(self.net[0], Conv2d)):
             return None
-        specs, params, i, cin = [], [], 0, y.shape[1]
+        specs, params, i, cin = [], [], 0, self.net[0].out_channels
         while i < len(layers):
             conv = layers[i]
             if not (isinstance(conv, Conv2d) and conv.padding == (0, 0) and conv.dilation == (1, 1) and conv.groups == 1
@@ -124,14 +125,15 @@ class Backbone(Module):
             params += [conv.weight, conv.bias]
             cin = conv.out_channels
             i += 2 if relu else 1
-        return ops.ConvTailFunction.apply(y, tuple(specs), *params) if specs else None
+        return (tuple(specs), params) if specs else None
 
     def forward(self, x):
-        y = self._fused_stem(x)
+        from . import ops
+        tail = self._gemm_tail_plan(x)
+        y = self._fused_stem(x, channels_last=tail is not None)
         if y is not None:
-            tail = self._gemm_tail(y)
-            if tail is not None:
-                return tail
+            if tail is not None:      # the stem wrote channels-last: conv_1 reads it as it is
+                return ops.ConvTailFunction.apply(y, tail[0], True, *tail[1])
             for layer in list(self.net)[2:]:
                 y = layer(y)
             return y

@@ -404,24 +404,26 @@ class StemConvFunction(torch.autograd.Function):
     leaf without grad; callers that need d_x keep the library path)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int):
+    def forward(ctx, x, weight, bias, stride: int, pad_t: int, pad_l: int, Ho: int, Wo: int, channels_last: bool = False):
         x = x.contiguous()
         w = weight.detach().contiguous()
-        y = torch.empty(x.shape[0], w.shape[0], Ho, Wo, device=x.device, dtype=torch.float32)
-        K.stem_conv_fwd(x, w, bias.detach().contiguous(), stride, pad_t, pad_l, Ho, Wo, y)
+        # channels_last: [B,Ho,Wo,Cout], the layout ConvTailFunction works in (no transpose pass between the two)
+        shape = (x.shape[0], Ho, Wo, w.shape[0]) if channels_last else (x.shape[0], w.shape[0], Ho, Wo)
+        y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        K.stem_conv_fwd(x, w, bias.detach().contiguous(), stride, pad_t, pad_l, Ho, Wo, y, channels_last)
         ctx.save_for_backward(x, y)
-        ctx.geom = (stride, pad_t, pad_l, tuple(w.shape))
+        ctx.geom = (stride, pad_t, pad_l, tuple(w.shape), channels_last)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
-        stride, pad_t, pad_l, w_shape = ctx.geom
+        stride, pad_t, pad_l, w_shape, channels_last = ctx.geom
         d_w = torch.empty(w_shape, device=x.device, dtype=torch.float32)
         d_b = torch.empty(w_shape[0], device=x.device, dtype=torch.float32)
         ws = K.stem_bwd_workspace(x.shape[1], w_shape[0], x.device)
-        K.stem_conv_bwd(x, y, dy.contiguous(), w_shape, stride, pad_t, pad_l, ws, d_w, d_b)
-        return None, d_w, d_b, None, None, None, None, None
+        K.stem_conv_bwd(x, y, dy.contiguous(), w_shape, stride, pad_t, pad_l, ws, d_w, d_b, channels_last)
+        return None, d_w, d_b, None, None, None, None, None, None
 
 
 class ConvTailFunction(torch.autograd.Function):
@@ -434,14 +436,17 @@ class ConvTailFunction(torch.autograd.Function):
     warp reads the patches with TMA im2col loads (forward and weight gradient; no patch matrix in HBM), bias + ReLU run in
     the GEMM epilogue, and the input gradient is dgrad on the same kernel plus the transposed patch gather (csrc/conv.cu).  Layers: padding 0, dilation 1, groups 1, square kernel, Cin % 4 == 0.
 
-    forward(y0 [B,C0,H0,W0] NCHW (the stem's output), specs, *weights_and_biases) -> feat [B,F,Hc,Wc] NCHW;
-    ``specs`` = ((k, stride, relu), ...)."""
+    forward(y0 (the stem's output: [B,C0,H0,W0] NCHW, or already channels-last [B,H0,W0,C0] with ``nhwc_in``), specs,
+    nhwc_in, *weights_and_biases) -> feat [B,F,Hc,Wc] NCHW; ``specs`` = ((k, stride, relu), ...)."""
 
     @staticmethod
-    def forward(ctx, y0, specs, *params):
-        B0, C0, H0, W0 = y0.shape
-        x = torch.empty(B0, H0, W0, C0, device=y0.device, dtype=torch.float32)      # channels-last from here on
-        K.transpose_batched(y0.contiguous().view(B0, C0, H0 * W0), x.view(B0, H0 * W0, C0))
+    def forward(ctx, y0, specs, nhwc_in, *params):
+        if nhwc_in:
+            x = y0.contiguous()                 # the stem wrote channels-last: no transpose pass
+        else:
+            B0, C0, H0, W0 = y0.shape
+            x = torch.empty(B0, H0, W0, C0, device=y0.device, dtype=torch.float32)      # channels-last from here on
+            K.transpose_batched(y0.contiguous().view(B0, C0, H0 * W0), x.view(B0, H0 * W0, C0))
         saved, shapes, split = [], [], []
         for li, (k, s, relu) in enumerate(specs):
             w, b = params[2 * li].detach(), params[2 * li + 1].detach().contiguous()
@@ -466,7 +471,7 @@ class ConvTailFunction(torch.autograd.Function):
             shapes.append((Bn, H, W, Cin, Ho, Wo, tuple(w.shape)))
             x = y.view(Bn, Ho, Wo, w.shape[0])
         ctx.save_for_backward(*saved)
-        ctx.specs, ctx.shapes, ctx.split = specs, shapes, split
+        ctx.specs, ctx.shapes, ctx.split, ctx.nhwc_in = specs, shapes, split, nhwc_in
         Bn, Ho, Wo, F = x.shape
         feat = torch.empty(Bn, F, Ho, Wo, device=x.device, dtype=torch.float32)
         K.transpose_batched(x.view(Bn, Ho * Wo, F), feat.view(Bn, F, Ho * Wo))
@@ -494,7 +499,7 @@ class ConvTailFunction(torch.autograd.Function):
             grads[2 * li] = d_wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2).contiguous()
             grads[2 * li + 1] = db
             if li == 0 and not ctx.needs_input_grad[0]:
-                return (None, None) + tuple(grads)
+                return (None, None, None) + tuple(grads)
             if implicit and K.conv_dgrad_supported(k, s, wshape[0]):
                 # transposed convolution as s*s implicit GEMMs over dy (no d_col matrix, no scatter pass)
                 w4 = wr.view(wshape[0], k, k, Cin).permute(0, 3, 1, 2)
@@ -511,9 +516,11 @@ class ConvTailFunction(torch.autograd.Function):
                 K.col2im_nhwc(da, k, s, dx)
                 dy = dx.view(Bn * H * W, Cin)
         Bn, H, W, Cin = shapes[0][:4]
+        if ctx.nhwc_in:
+            return (dy.view(Bn, H, W, Cin), None, None) + tuple(grads)
         d_y0 = torch.empty(Bn, Cin, H, W, device=dy.device, dtype=torch.float32)
         K.transpose_batched(dy.view(Bn, H * W, Cin), d_y0.view(Bn, Cin, H * W))
-        return (d_y0, None) + tuple(grads)
+        return (d_y0, None, None) + tuple(grads)
 
 
 class CellSweepFunction(torch.autograd.Function):

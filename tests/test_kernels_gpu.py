@@ -439,6 +439,13 @@ def test_stem_conv_vs_torch_cpu(B, C, I, stride, pad):
     assert_close(got, want, "stem forward")
     helpers.assert_close(wd.grad.cpu(), w.grad, "stem d_weight", atol=helpers.ATOL + helpers.RTOL * float(w.grad.norm()) / w.grad.numel() ** 0.5)
     helpers.assert_close(bd.grad.cpu(), b.grad, "stem d_bias", atol=helpers.ATOL + helpers.RTOL * float(b.grad.norm()) / b.grad.numel() ** 0.5)
+    # channels-last variant (the layout the GEMM tail consumes): the same values, forward and backward, bit for bit
+    wn, bn = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+    got_cl = ops.StemConvFunction.apply(x.to(DEV), wn, bn, stride, pt, pl, want.shape[2], want.shape[3], True)
+    assert got_cl.shape == (B, want.shape[2], want.shape[3], 128)
+    got_cl.backward(cot.to(DEV).permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(got_cl.permute(0, 3, 1, 2), got), "channels-last stem forward"
+    assert torch.equal(wn.grad, wd.grad) and torch.equal(bn.grad, bd.grad), "channels-last stem backward"
 
 
 def test_backbone_uses_fused_stem_and_matches_library_path():
