@@ -534,8 +534,18 @@ __global__ void __launch_bounds__(256) relu_fixup_conv_kernel(const float* __res
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long mn, int N, const float* __restrict__ bias,
                                      float* __restrict__ C, int ldc) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (long long)gridDim.x * blockDim.x) {
+        // the partial sums are added in split order (reproducible); the loads of eight splits are issued together — a thread
+        // that waits for one L2 round trip per split made every one of these 21 launches per step a 15 us latency chain
         float acc = ws[i];
-        for (int s = 1; s < splits; ++s) acc += ws[(long long)s * mn + i];
+        int s = 1;
+        for (; s + 8 <= splits; s += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcs(ws + (long long)(s + j) * mn + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += v[j];
+        }
+        for (; s < splits; ++s) acc += ws[(long long)s * mn + i];
         const int n = (int)(i % N);
         const long long m = i / N;
         if (bias) acc += bias[n];
