@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libspair_b200.so")
 SOURCES = ["heads.cu", "glimpse.cu", "render.cu", "kl.cu", "sweep.cu", "stem.cu", "gemm.cu", "conv.cu"]
-HEADERS = ["common.cuh", "warp_math.cuh", os.path.join("..", "..", "include", "spair_b200.h")]
+HEADERS = ["common.cuh", "warp_math.cuh", "sweep_tc.cuh", os.path.join("..", "..", "include", "spair_b200.h")]
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "shared"]
 
