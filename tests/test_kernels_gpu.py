@@ -419,6 +419,51 @@ def test_sweep_weight_packing_is_exact(shapes):
         assert torch.equal(b.cpu().view(n4, k, 4), wb.view(n4, 4, k).permute(0, 2, 1)), "backward layout"
 
 
+def _tf32_round_bits(x):
+    """(bits + 0x1000) & 0xffffe000 on the raw fp32 pattern: nearest TF32, ties away from zero (csrc/sweep_tc.cuh tf32_round)."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+@pytest.mark.parametrize("shapes", [
+    [(100, 324), (100, 100), (108, 100), (256, 784), (128, 256), (100, 128), (100, 478), (100, 100), (102, 100), (100, 479), (100, 100), (1, 100)],
+    [(40, 70), (33, 40), (12, 33), (256, 2352), (130, 256), (20, 130), (64, 90), (64, 64), (6, 64), (64, 91), (31, 64), (1, 31)]])
+def test_tensor_core_sweep_weight_streams_are_exact(shapes):
+    """spair_sweep_tc_pack: both weight streams of the tensor-core sweeps, stage by stage in the order tc::mma_loop consumes
+    them (layer -> accumulator group of 8 feature tiles -> chunk of 8 k-blocks -> tile -> k-block); a stage = 128 features x
+    32 reduction indices as the TF32 hi tile then the lo tile, rows of 128 bytes with the 16-byte chunks XOR-swizzled by the
+    row (the K-major SWIZZLE_128B operand image), zero padded.  hi = TF32(w), lo = TF32(w - hi); the backward stream holds
+    W^T tiles in the order obj, z, enc, box x layers 2, 1, 0.  The second shape set has a 2352-wide layer (config D's
+    encoder: 19 feature tiles backward = three accumulator groups) and ragged tails everywhere."""
+    rs = gen(9)
+    ws = [torch.randn(n, k, generator=rs) * 0.3 for n, k in shapes]
+    packed = K().PackedSweepWeightsTC([w.to(DEV) for w in ws])
+    fl = torch.arange(128).view(128, 1)
+    kl = torch.arange(32).view(1, 32)
+    pos = (fl * 32 + ((((kl >> 2) ^ fl) & 7) << 2) + (kl & 3)).flatten()       # where element (fl, kl) of a tile lives
+    for backward, stream in ((False, packed.fwd.cpu()), (True, packed.bwd.cpu())):
+        stage = 0
+        for e in range(12):
+            l = 3 * (3 - e // 3) + (2 - e % 3) if backward else e
+            W = ws[l].t().contiguous() if backward else ws[l]                   # [features, reduction]
+            M, Kd = W.shape
+            KB, tiles, chunks = (Kd + 31) // 32, (M + 127) // 128, (Kd + 255) // 256
+            Wp = torch.zeros(tiles * 128, KB * 32)
+            Wp[:M, :Kd] = W
+            hi = _tf32_round_bits(Wp)
+            lo = _tf32_round_bits(Wp - hi)
+            for g0 in range(0, tiles, 8):
+                for c in range(chunks):
+                    for mt in range(g0, min(g0 + 8, tiles)):
+                        for kb in range(8 * c, min(8 * c + 8, KB)):
+                            got = stream[stage * 8192:(stage + 1) * 8192]
+                            want_hi = hi[mt * 128:(mt + 1) * 128, kb * 32:(kb + 1) * 32].flatten()
+                            want_lo = lo[mt * 128:(mt + 1) * 128, kb * 32:(kb + 1) * 32].flatten()
+                            assert torch.equal(got[:4096][pos], want_hi), ("hi", backward, e, mt, kb)
+                            assert torch.equal(got[4096:][pos], want_lo), ("lo", backward, e, mt, kb)
+                            stage += 1
+        assert stage * 8192 == stream.numel()
+
+
 @pytest.mark.parametrize("B,C,I,stride,pad", [(3, 1, 128, 3, (9, 14, 9, 14)), (2, 3, 64, 2, (7, 7, 7, 7)), (2, 1, 37, 3, (2, 5, 1, 3)),
                                               (5, 3, 41, 1, (0, 0, 0, 0))])
 def test_stem_conv_vs_torch_cpu(B, C, I, stride, pad):
