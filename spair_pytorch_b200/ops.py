@@ -706,22 +706,26 @@ class CellSweepFunction(torch.autograd.Function):
                            P, dXz[:, c_pt:], box_mlp.dY[r0:r1])
             box_mlp.backward_dx(r0, r1)
 
-        # ---- gradients of shared inputs, accumulated over all rows at once ----
-        d_in = box_mlp.dX[:, :F + CTX] + z_mlp.dX[:, :F + CTX] + obj_mlp.dX[:, :F + CTX]     # [rows, F+CTX]
-        d_in = d_in.view(HW, B, F + CTX)
-        # backbone features: wavefront-major rows -> [B,F,Hc,Wc]
-        d_feat = d_in[:, :, :F].index_select(0, plan.gather_index).permute(1, 2, 0).reshape(B, F, s.Hc, s.Wc)
-        # virtual edge element: every (cell, slot) whose neighbour is outside the grid (models.py:316)
-        n_nb = len(s.offsets)
-        d_edge = (d_in[:, :, F:].reshape(HW, B, n_nb, E) * plan.missing_dev[:, None, :, None]).sum((0, 1, 2))
+        # ---- after the sweep: the gradients of the shared inputs (what the backbone's backward waits for) on this stream, and,
+        # at the same time on four side streams, the weight gradients: 12 skinny GEMMs (<= 256 x 784 outputs, reduction over
+        # all HW*B rows), one stream per network (forked from / joined to the current stream with events, which CUDA-graph
+        # capture records as parallel branches)
+        shared = {}
 
-        # ---- weight gradients: 12 skinny GEMMs (<= 256 x 784 outputs, reduction over all HW*B rows).  cuBLAS runs each
-        # as a split-K grid of ~70 CTAs, half of the 148 SMs, so the four networks go to four streams and overlap
-        # (forked from / joined to the current stream with events, which CUDA-graph capture records as parallel branches).
+        def shared_input_grads():
+            d_in = box_mlp.dX[:, :F + CTX] + z_mlp.dX[:, :F + CTX] + obj_mlp.dX[:, :F + CTX]     # [rows, F+CTX]
+            d_in = d_in.view(HW, B, F + CTX)
+            # backbone features: wavefront-major rows -> [B,F,Hc,Wc]
+            shared["feat"] = d_in[:, :, :F].index_select(0, plan.gather_index).permute(1, 2, 0).reshape(B, F, s.Hc, s.Wc)
+            # virtual edge element: every (cell, slot) whose neighbour is outside the grid (models.py:316)
+            n_nb = len(s.offsets)
+            shared["edge"] = (d_in[:, :, F:].reshape(HW, B, n_nb, E) * plan.missing_dev[:, None, :, None]).sum((0, 1, 2))
+
         all_mlps = (box_mlp, enc_mlp, z_mlp, obj_mlp)
         for mlp in all_mlps:
             mlp.alloc_weight_grads()
-        K.parallel_branches(x.device, plan.side_streams, [mlp.weight_grads for mlp in all_mlps])
+        K.parallel_branches(x.device, plan.side_streams, [shared_input_grads] + [mlp.weight_grads for mlp in all_mlps])
+        d_feat, d_edge = shared["feat"], shared["edge"]
 
         grads = []
         for mlp, n_heads, head_sizes in ((box_mlp, 2, (8, P)), (enc_mlp, 1, None), (z_mlp, 2, (2, P)), (obj_mlp, 1, None)):
