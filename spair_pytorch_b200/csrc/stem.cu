@@ -108,25 +108,25 @@ __global__ void __launch_bounds__(kStemFwdThreads) stem_fwd_kernel(StemArgs p) {
         }
     } else {
 #pragma unroll 2
-    for (int o = 0; o < kStemCout; ++o) {
-        float acc[PP];
+        for (int o = 0; o < kStemCout; ++o) {
+            float acc[PP];
 #pragma unroll
-        for (int j = 0; j < PP; ++j) acc[j] = b_s[o];
+            for (int j = 0; j < PP; ++j) acc[j] = b_s[o];
 #pragma unroll
-        for (int t4 = 0; t4 < T / 4; ++t4) {
-            const float4 w = *reinterpret_cast<const float4*>(w_s + o * T + 4 * t4);
+            for (int t4 = 0; t4 < T / 4; ++t4) {
+                const float4 w = *reinterpret_cast<const float4*>(w_s + o * T + 4 * t4);
 #pragma unroll
-            for (int j = 0; j < PP; ++j) {
-                acc[j] = fmaf(w.x, tap[j][4 * t4 + 0], acc[j]);
-                acc[j] = fmaf(w.y, tap[j][4 * t4 + 1], acc[j]);
-                acc[j] = fmaf(w.z, tap[j][4 * t4 + 2], acc[j]);
-                acc[j] = fmaf(w.w, tap[j][4 * t4 + 3], acc[j]);
+                for (int j = 0; j < PP; ++j) {
+                    acc[j] = fmaf(w.x, tap[j][4 * t4 + 0], acc[j]);
+                    acc[j] = fmaf(w.y, tap[j][4 * t4 + 1], acc[j]);
+                    acc[j] = fmaf(w.z, tap[j][4 * t4 + 2], acc[j]);
+                    acc[j] = fmaf(w.w, tap[j][4 * t4 + 3], acc[j]);
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < PP; ++j)
-            if (valid[j]) yb[(size_t)o * npix + pix0 + j * kStemFwdThreads] = fmaxf(acc[j], 0.0f);
-    }
+            for (int j = 0; j < PP; ++j)
+                if (valid[j]) yb[(size_t)o * npix + pix0 + j * kStemFwdThreads] = fmaxf(acc[j], 0.0f);
+        }
     }
 }
 
