@@ -287,10 +287,9 @@ def kernel_roofline(net, x, steps=20):
         if sweep_ms[k]:
             ms = statistics.mean(sweep_ms[k])
             tf = 2 * macs * N / (ms * 1e-3) / 1e12
-            mode = os.environ.get("SPAIR_SWEEP_TC", "auto")
             mc = plan.schedule.max_cells              # rows per CTA and wavefront, as ops.CellSweepFunction chooses images per CTA
             rows = mc * (max(1, min(2, 16 // mc)) if B > 148 else 1)
-            on_tc = mode == "1" or (k == "bwd" and (mode == "bwd" or (mode == "auto" and rows >= 12)))
+            on_tc = ops.sweep_tc_choice(rows)[0 if k == "fwd" else 1]
             out[label] = {"ms": ms, "flops": 2 * macs * N, "achieved": tf, "frac": tf / fpeak, "bound": "fp32",
                           "unit": "TFLOP/s", "peak": fpeak,
                           "dense_layers": "tcgen05 kind::tf32, hi/lo split (csrc/sweep_tc.cuh)" if on_tc else "fp32 SIMT FFMA",

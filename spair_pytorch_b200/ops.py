@@ -37,6 +37,19 @@ USE_TENSOR_CORE_GEMM = "SPAIR_NO_TC_GEMM" not in _os.environ
 IMPLICIT_CONV = "SPAIR_EXPLICIT_IM2COL" not in _os.environ
 
 
+def sweep_tc_choice(rows_per_cta: int, mode: Optional[str] = None):
+    """(forward, backward): which of the two fused sweeps run their dense layers on the tensor cores (csrc/sweep_tc.cuh).
+    ``mode`` = SPAIR_SWEEP_TC: "auto" (default) -> the backward sweep when a CTA has >= 12 rows per wavefront (the cost of
+    the tensor-core layers does not depend on the rows, that of the SIMT layers does: 16 rows 2.39 vs 2.65 ms, 8 rows 2.48 vs
+    2.27 ms); "bwd" -> the backward always; "1" -> both (the forward is then ~1e-6 accurate, not parity-exact, DESIGN.md
+    section 5); "0" -> neither."""
+    if mode is None:
+        mode = _os.environ.get("SPAIR_SWEEP_TC", "auto")
+    if mode not in ("auto", "bwd", "1", "0"):
+        raise ValueError("SPAIR_SWEEP_TC must be auto, bwd, 1 or 0, got %r" % mode)
+    return mode == "1", mode in ("1", "bwd") or (mode == "auto" and rows_per_cta >= 12)
+
+
 def _timed_launch(name, fn, *args, **kwargs):
     if SWEEP_EVENTS is None:
         return fn(*args, **kwargs)
@@ -592,9 +605,7 @@ class CellSweepFunction(torch.autograd.Function):
             # 1 or 16 rows (MMA issue interval) while the SIMT layers scale with the rows, so the default ("auto") takes
             # them only when a CTA has >= 12 rows per wavefront (measured: 16 rows 2.39 vs 2.65 ms, 8 rows 2.48 vs 2.27 ms).
             # SPAIR_SWEEP_TC=1: both sweeps; =bwd: backward always; =0: neither.
-            mode = _os.environ.get("SPAIR_SWEEP_TC", "auto")
-            tc_fwd = mode == "1"
-            tc_bwd = mode in ("1", "bwd") or (mode == "auto" and s.max_cells * ipc >= 12)
+            tc_fwd, tc_bwd = sweep_tc_choice(s.max_cells * ipc)
             weights = [w for m in mlps for w in m.W]
             packed = None if (tc_fwd and tc_bwd) else K.PackedSweepWeights(weights)     # one launch each; kept for backward
             packed_tc = K.PackedSweepWeightsTC(weights, forward=tc_fwd, backward=tc_bwd) if (tc_fwd or tc_bwd) else None

@@ -83,3 +83,25 @@ def test_flat_parameter_adam_equals_per_tensor_adam():
         opt_ref.step()
         for p, q in zip(net.parameters(), ref.parameters()):
             assert torch.equal(p, q), "update %d differs" % it
+
+
+def test_sweep_tensor_core_mode_selection(monkeypatch):
+    """Which sweep runs its dense layers on the tensor cores (ops.sweep_tc_choice; SPAIR_SWEEP_TC): by default only the
+    backward sweep, and only when a CTA has >= 12 rows per wavefront; the forward never unless asked for (it is not
+    parity-exact on tcgen05)."""
+    from spair_pytorch_b200 import ops
+    monkeypatch.delenv("SPAIR_SWEEP_TC", raising=False)
+    assert ops.sweep_tc_choice(16) == (False, True) and ops.sweep_tc_choice(12) == (False, True)
+    assert ops.sweep_tc_choice(8) == (False, False) and ops.sweep_tc_choice(6) == (False, False)
+    assert ops.sweep_tc_choice(6, "bwd") == (False, True)
+    assert ops.sweep_tc_choice(16, "0") == (False, False)
+    assert ops.sweep_tc_choice(4, "1") == (True, True)
+    monkeypatch.setenv("SPAIR_SWEEP_TC", "1")
+    assert ops.sweep_tc_choice(16) == (True, True)
+    monkeypatch.setenv("SPAIR_SWEEP_TC", "yes")
+    try:
+        ops.sweep_tc_choice(16)
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("an unknown SPAIR_SWEEP_TC value must be rejected")
